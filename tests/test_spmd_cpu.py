@@ -1,0 +1,93 @@
+"""N>1 control plane on CPU: two processes bootstrap an SPMD store over a TCPStore rendezvous
+(gloo-style, no GPU), each hosting its own volume; objects put on one rank are visible on the
+other; shutdown is coordinated (reference tests/test_spmd.py:251-374)."""
+
+import asyncio
+import json
+import os
+import socket
+import tempfile
+
+import pytest
+import torch.multiprocessing as mp
+
+from torchstore_b200.spmd import SPMDEnv
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, outdir):
+    os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
+    import torch.distributed as dist
+
+    import torchstore_b200 as ts
+
+    async def main():
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port + 1}", rank=rank, world_size=world)
+        await ts.initialize_spmd(ts.LocalRankStrategy())
+        res = {}
+        await ts.put(f"from_{rank}", {"rank": rank, "payload": list(range(rank + 3))})
+        dist.barrier()
+        other = (rank + 1) % world
+        res["peer"] = await ts.get(f"from_{other}")
+        res["keys"] = sorted(await ts.keys())
+        c = await ts.client()
+        vm = await c._controller.locate_volumes.call_one([f"from_{rank}"])
+        res["my_volume"] = list(vm[f"from_{rank}"].keys())
+        # state dict of objects written by rank 0, read by rank 1
+        if rank == 0:
+            await ts.put_state_dict({"step": 11, "cfg": {"a": 1}}, "sd")
+        dist.barrier()
+        res["sd"] = await ts.get_state_dict("sd")
+        res["exists_missing"] = await ts.exists("nope")
+        dist.barrier()
+        await ts.shutdown()
+        dist.destroy_process_group()
+        with open(os.path.join(outdir, f"{rank}.json"), "w") as f:
+            json.dump(res, f)
+
+    asyncio.run(main())
+
+
+def test_two_rank_spmd_store_on_cpu():
+    world = 2
+    port = _free_port()
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, port, d), nprocs=world, join=True)
+        out = [json.load(open(os.path.join(d, f"{r}.json"))) for r in range(world)]
+    for r in range(world):
+        other = (r + 1) % world
+        assert out[r]["peer"] == {"rank": other, "payload": list(range(other + 3))}
+        assert out[r]["keys"][:2] == ["from_0", "from_1"]
+        assert out[r]["my_volume"] == [str(r)]
+        assert out[r]["sd"] == {"step": 11, "cfg": {"a": 1}}
+        assert out[r]["exists_missing"] is False
+
+
+def test_spmd_env_parsing(monkeypatch):
+    for k, v in {"RANK": "3", "LOCAL_RANK": "1", "WORLD_SIZE": "8", "LOCAL_WORLD_SIZE": "4", "MASTER_ADDR": "h",
+                 "MASTER_PORT": "1234"}.items():
+        monkeypatch.setenv(k, v)
+    env = SPMDEnv.from_env()
+    assert (env.rank, env.local_rank, env.world_size, env.num_hosts, env.group_rank) == (3, 1, 8, 2, 0)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "3")
+    with pytest.raises(ValueError):
+        SPMDEnv.from_env()
+    monkeypatch.delenv("RANK")
+    with pytest.raises(RuntimeError, match="requires the RANK env var"):
+        SPMDEnv.from_env()
+
+
+def test_spmd_requires_explicit_strategy():
+    import torchstore_b200 as ts
+
+    with pytest.raises(RuntimeError, match="explicit HostStrategy or LocalRankStrategy"):
+        asyncio.run(ts.initialize_spmd(None))

@@ -29,7 +29,7 @@ def time_plan(pairs, iters=10, warmup=3, flush=None):
     rects, n = build_rects([(StridedMem.from_tensor(s), StridedMem.from_tensor(d)) for s, d in pairs])
     plan = _native.plan_create(0, rects, n)
     info = _native.plan_info(plan).as_dict()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _native.torch_stream(0)
     times = []
     for i in range(warmup + iters):
         if flush is not None:

@@ -306,6 +306,17 @@ def plan_compile_host(device: int, rects, n: int, flags: int = 0, tile_units: in
     return rect_buf[: n_rects.value * 192], tile_buf[: n_tiles.value], info
 
 
+CUDA_STREAM_LEGACY = 0x1  # cudaStreamLegacy: an explicit handle for the default stream
+
+
+def torch_stream(device: int | None = None) -> int:
+    """cudaStream_t of torch's current stream as a value the C-ABI can take.  torch reports the
+    legacy default stream as 0, which the ABI reserves for "the library's copy stream"; map it to
+    the explicit cudaStreamLegacy handle."""
+    h = torch.cuda.current_stream(device).cuda_stream
+    return h if h else CUDA_STREAM_LEGACY
+
+
 def copy_stream(device: int) -> int:
     out = C.c_void_p()
     check(lib().tsb_copy_stream(device, C.byref(out)))

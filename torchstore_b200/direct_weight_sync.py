@@ -57,7 +57,7 @@ async def wait_event(event: "_native.Event") -> None:
 def _fence_in(device: int) -> None:
     """Copy stream waits for whatever torch has queued on the caller's current stream."""
     ev = _native.Event(device)
-    ev.record(torch.cuda.current_stream(device).cuda_stream)
+    ev.record(_native.torch_stream(device))
     ev.wait_on(device, None)
     ev.close()
 
@@ -238,6 +238,14 @@ class DirectWeightSyncSource:
             ev.close()
         return len(self._staging)
 
+    def fence(self) -> None:
+        """Make every write queued on the caller's streams (optimizer step, staging refresh) land in
+        HBM before readers are told to pull.  The reference has no such fence (its RDMA reads race
+        with in-flight kernels); on one box it costs a stream sync."""
+        devices = {h.rdma_buffer.device for h in self._handles.values()}
+        for dev in devices:
+            torch.cuda.current_stream(dev).synchronize()
+
     def _drop_plans(self) -> None:
         for plan in self._refresh_plans.values():
             try:
@@ -398,7 +406,7 @@ class DirectWeightSyncDest:
             _native.plan_run(plan, None)
             done = _native.Event(dev, timing=True).record(None)
             # later work on the caller's stream sees the new weights even if it does not host-wait
-            done.wait_on(dev, torch.cuda.current_stream(dev).cuda_stream)
+            done.wait_on(dev, _native.torch_stream(dev))
             events[dev] = (start, done)
         return events
 

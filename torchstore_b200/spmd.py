@@ -1,0 +1,195 @@
+"""torchrun-style bootstrap without Monarch (reference torchstore/spmd.py:43-362).
+
+Every rank calls ``await initialize(strategy)``.  Each rank starts one ``ActorServer`` thread and
+hosts its own storage volume (LocalRankStrategy: volume id == rank, tensors in that rank's GPU);
+rank 0 also hosts the controller.  Handles are exchanged through a ``TCPStore`` rendezvous on
+MASTER_ADDR:MASTER_PORT (the store torchrun's agent already serves, when there is one).
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import socket
+from dataclasses import dataclass
+from datetime import timedelta
+from typing import Any
+
+import torch
+from torch.distributed import TCPStore
+
+import torchstore_b200.api as _api
+from torchstore_b200 import rpc
+from torchstore_b200 import strategy as strategy_mod
+from torchstore_b200.controller import Controller
+from torchstore_b200.storage_volume import StorageVolume
+from torchstore_b200.strategy import HostStrategy, LocalRankStrategy, TorchStoreStrategy
+
+logger = logging.getLogger(__name__)
+
+
+def _spmd_key(store_name: str, suffix: str) -> str:
+    return f"torchstore/spmd/{store_name}/{suffix}"
+
+
+@dataclass(frozen=True)
+class SPMDEnv:
+    rank: int
+    local_rank: int
+    world_size: int
+    local_world_size: int
+    master_addr: str
+    master_port: int
+
+    @property
+    def num_hosts(self) -> int:
+        return self.world_size // self.local_world_size
+
+    @property
+    def group_rank(self) -> int:
+        return self.rank // self.local_world_size
+
+    @staticmethod
+    def _parse(name: str, default: str | None = None) -> str:
+        value = os.environ.get(name, default)
+        if value is None:
+            raise RuntimeError(f"SPMD TorchStore initialization requires the {name} env var")
+        return value
+
+    @classmethod
+    def from_env(cls, *, master_addr: str | None = None, master_port: int | None = None) -> "SPMDEnv":
+        rank = int(cls._parse("RANK"))
+        local_rank = int(cls._parse("LOCAL_RANK"))
+        world_size = int(cls._parse("WORLD_SIZE"))
+        local_world_size = int(cls._parse("LOCAL_WORLD_SIZE", str(world_size)))
+        if world_size % local_world_size != 0:
+            raise ValueError(f"world_size ({world_size}) must be divisible by local_world_size ({local_world_size})")
+        return cls(rank=rank, local_rank=local_rank, world_size=world_size, local_world_size=local_world_size,
+                   master_addr=cls._parse("MASTER_ADDR", master_addr),
+                   master_port=int(cls._parse("MASTER_PORT", None if master_port is None else str(master_port))))
+
+
+class _SPMDSession:
+    """Per-process resources of an SPMD store; ``rendezvous`` is reusable by callers."""
+
+    def __init__(self, *, rendezvous, controller, store_name: str, is_primary: bool, env: SPMDEnv,
+                 owned_actors: list[str]) -> None:
+        self.rendezvous = rendezvous
+        self.controller = controller
+        self.is_primary = is_primary
+        self.env = env
+        self._store_name = store_name
+        self._owned = owned_actors
+
+    async def shutdown(self) -> None:
+        """Coordinated teardown: every rank checks in, rank 0 tears the controller down and
+        publishes the outcome, the others wait for it.  Safe to call twice."""
+        if _api._spmd_state_map.pop(self._store_name, None) is None:
+            return
+        name = self._store_name
+        err: Exception | None = None
+        try:
+            self.rendezvous.add(_spmd_key(name, "shutdown_arrivals"), 1)
+            if self.is_primary:
+                status = "ok"
+                try:
+                    # wait until every rank stopped issuing requests
+                    import time
+
+                    deadline = time.time() + 120
+                    while self.rendezvous.add(_spmd_key(name, "shutdown_arrivals"), 0) < self.env.world_size:
+                        if time.time() > deadline:
+                            raise RuntimeError("Timed out waiting for all ranks to reach shutdown")
+                        time.sleep(0.002)
+                    await self.controller.teardown.call()
+                except Exception as e:  # noqa: BLE001
+                    err, status = e, repr(e)
+                self.rendezvous.set(_spmd_key(name, "shutdown"), status)
+            else:
+                try:
+                    status = self.rendezvous.get(_spmd_key(name, "shutdown")).decode()
+                except Exception as e:
+                    raise RuntimeError("Timed out waiting for TorchStore shutdown") from e
+                if status != "ok":
+                    raise RuntimeError(f"TorchStore SPMD shutdown failure - '{name}': {status}")
+        finally:
+            from torchstore_b200 import state_dict_utils
+
+            cl = _api._local_clent_map.get(name)
+            if cl is not None:
+                state_dict_utils.reset_direct_cache(cl)
+                cl.strategy.transport_context.clear()
+            _api.reset_client(name)
+            for actor in self._owned:
+                rpc.unregister_actor(actor)
+        if err is not None:
+            raise err
+
+
+def _validate_strategy(strategy) -> HostStrategy | LocalRankStrategy:
+    if isinstance(strategy, (HostStrategy, LocalRankStrategy)):
+        return strategy
+    raise RuntimeError("SPMD mode requires an explicit HostStrategy or LocalRankStrategy")
+
+
+def _open_rendezvous(env: SPMDEnv, timeout: timedelta):
+    # under torchrun the elastic agent already serves a TCPStore on MASTER_PORT: join it as a client
+    agent_store = os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "False") == "True"
+    return TCPStore(env.master_addr, env.master_port, env.world_size,
+                    is_master=(env.rank == 0 and not agent_store), timeout=timeout, wait_for_workers=False)
+
+
+async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str = _api.DEFAULT_TORCHSTORE_NAME, *,
+                     env: SPMDEnv | None = None, rendezvous_timeout: timedelta = timedelta(seconds=120),
+                     transport: str = "ipc", monarch_port: int = 26600, rendezvous=None) -> None:
+    """Initialize TorchStore from RANK / LOCAL_RANK / WORLD_SIZE / LOCAL_WORLD_SIZE / MASTER_ADDR /
+    MASTER_PORT.  One volume per rank (LocalRankStrategy) or per host (HostStrategy).
+
+    ``transport`` / ``monarch_port`` are accepted for signature compatibility (the control plane is
+    localhost sockets on one box).  ``rendezvous`` may pass an existing c10d store."""
+    strategy = _validate_strategy(strategy)
+    if store_name in _api._spmd_state_map:
+        raise RuntimeError(f"TorchStore '{store_name}' is already initialized")
+    if env is None:
+        env = SPMDEnv.from_env()
+    os.environ.setdefault("HOSTNAME", socket.gethostname())
+    if rendezvous is None:
+        rendezvous = _open_rendezvous(env, rendezvous_timeout)
+
+    server = rpc.ActorServer.instance()
+    owned: list[str] = []
+    hosts_volume = isinstance(strategy, LocalRankStrategy) or env.local_rank == 0
+    if hosts_volume:
+        strategy_mod._spawn_rank[0] = env.rank if isinstance(strategy, LocalRankStrategy) else env.group_rank
+        device = env.local_rank if torch.cuda.is_available() else None
+        vol = StorageVolume(id_func=strategy.get_volume_id, device=device)
+        strategy_mod._spawn_rank[0] = 0
+        vol_name = f"{store_name}/volume/{env.rank}"
+        owned.append(vol_name)
+        vol_ref = rpc.register_actor(vol_name, vol)
+        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}"), pickle.dumps(vol_ref))
+    else:
+        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}"), pickle.dumps(None))
+
+    controller_key = _spmd_key(store_name, "controller")
+    if env.rank == 0:
+        members = []
+        for r in range(env.world_size):
+            ref = pickle.loads(rendezvous.get(_spmd_key(store_name, f"volume/{r}")))
+            if ref is not None:
+                members.append(({"gpus": r}, ref))
+        name = f"{store_name}/controller"
+        owned.append(name)
+        controller = rpc.register_actor(name, Controller())
+        await controller.init.call(strategy=strategy, num_storage_volumes=len(members),
+                                   storage_volumes=rpc.ActorMesh(members))
+        rendezvous.set(controller_key, pickle.dumps(controller))
+    else:
+        controller = pickle.loads(rendezvous.get(controller_key))
+    del server
+    _api._spmd_state_map[store_name] = _SPMDSession(rendezvous=rendezvous, controller=controller, store_name=store_name,
+                                                   is_primary=(env.rank == 0), env=env, owned_actors=owned)
+
+
+__all__ = ["SPMDEnv", "initialize"]
