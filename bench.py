@@ -54,55 +54,74 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every ~5 ms; falls back to
+    `nvidia-smi -lms` when pynvml is unavailable)."""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, device_index: int):
         self.device_index = device_index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, int, float]] = []
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.device_index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self._t = threading.Thread(target=self._read, daemon=True)
-            self._t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+        self._thread = threading.Thread(target=self._loop_nvml if self._nvml else self._loop_smi, daemon=True)
+        self._thread.start()
+
+    def _loop_nvml(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                try:
+                    power = nv.nvmlDeviceGetPowerUsage(self._handle) / 1000.0
+                except Exception:
+                    power = 0.0
+                self.samples.append((clk, reasons, power))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def _loop_smi(self):
+        fields = "clocks.sm,clocks.max.sm,power.draw"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.device_index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                self.samples.append((float(parts[0]), 0, float(parts[2])))
+                self.sm_max = float(parts[1])
+            except Exception:
+                pass
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                smax = float(parts[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=6)
+        clocks = [c for c, _, _ in self.samples]
+        bits = 0
+        for _, r, _ in self.samples:
+            bits |= r
+        reasons = sorted(name for name, mask in self.REASONS.items() if bits & mask)
+        return {"sm_mhz": statistics.median(clocks) if clocks else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(clocks), "power_w_max": max((p for _, _, p in self.samples), default=None),
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def emit(obj):
@@ -381,6 +400,8 @@ def run_ours(args):
         ev0 = _native.Event(local_rank, timing=True)
         ev1 = _native.Event(local_rank, timing=True)
         barrier()
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStart()
         ev0.record(copy_stream)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -391,6 +412,8 @@ def run_ours(args):
         ev1.record(copy_stream)
         ev1.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStop()
         dev_ms = ev0.elapsed_ms(ev1)
         barrier()
         launches = _native.launch_count() - launches0
@@ -402,53 +425,55 @@ def run_ours(args):
         kern_avg_max = allmax(kern_avg)
         total_launches = int(allsum(launches))
 
-        # ---- e2e: host inputs, public API, wall clock ------------------------------------------------
-        src_bytes = src_flat.numel() * 2
-        host_src = torch.empty(src_flat.numel(), dtype=torch.bfloat16).pin_memory()
-        host_src.copy_(src_flat.cpu())
-        # result sample: first row (<= 4096 elements) of every destination tensor, gathered by one
-        # copy_rects launch into a contiguous buffer and read back with one D2H copy
-        rows = []
-        for k, v in dst_local.items():
-            flat = v.reshape(-1) if v.dim() == 1 else v[0]
-            rows.append(flat[: min(4096, flat.numel())])
-        sample_dev = torch.zeros(sum(r.numel() for r in rows), dtype=torch.bfloat16, device=dev)
-        pairs, off = [], 0
-        for r in rows:
-            pairs.append((StridedMem.from_tensor(r), StridedMem.from_tensor(sample_dev[off:off + r.numel()])))
-            off += r.numel()
-        rects, nr = build_rects(pairs)
-        sample_plan = _native.plan_create(local_rank, rects, nr)
-        sample_host = torch.empty(sample_dev.numel(), dtype=torch.bfloat16).pin_memory()
-        d2h_bytes = sample_dev.numel() * 2
+        e2e_ms, e2e_launches, src_bytes, d2h_bytes = None, 0, 0, 0
+        if not args.no_e2e:
+            # ---- e2e: host inputs, public API, wall clock ------------------------------------------------
+            src_bytes = src_flat.numel() * 2
+            host_src = torch.empty(src_flat.numel(), dtype=torch.bfloat16).pin_memory()
+            host_src.copy_(src_flat.cpu())
+            # result sample: first row (<= 4096 elements) of every destination tensor, gathered by one
+            # copy_rects launch into a contiguous buffer and read back with one D2H copy
+            rows = []
+            for k, v in dst_local.items():
+                flat = v.reshape(-1) if v.dim() == 1 else v[0]
+                rows.append(flat[: min(4096, flat.numel())])
+            sample_dev = torch.zeros(sum(r.numel() for r in rows), dtype=torch.bfloat16, device=dev)
+            pairs, off = [], 0
+            for r in rows:
+                pairs.append((StridedMem.from_tensor(r), StridedMem.from_tensor(sample_dev[off:off + r.numel()])))
+                off += r.numel()
+            rects, nr = build_rects(pairs)
+            sample_plan = _native.plan_create(local_rank, rects, nr)
+            sample_host = torch.empty(sample_dev.numel(), dtype=torch.bfloat16).pin_memory()
+            d2h_bytes = sample_dev.numel() * 2
 
-        async def e2e_step():
-            # (1) new weights arrive from the host
-            _native.memcpy_async(local_rank, src_flat.data_ptr(), host_src.data_ptr(), src_bytes, _native.TSB_H2D, copy_stream)
-            _native.stream_sync(local_rank, copy_stream)
-            # (2) publish + pull through the public API
-            await ts.put_state_dict(None, KEY, direct_rdma=True)
-            if n > 1:
-                dist.barrier(device_ids=[local_rank])  # every source refreshed before anyone pulls
-            await ts.get_state_dict(KEY, user_state_dict=dst_sd, direct_rdma=True)
-            # (3) read the result sample back
-            _native.plan_run(sample_plan, copy_stream)
-            _native.memcpy_async(local_rank, sample_host.data_ptr(), sample_dev.data_ptr(), d2h_bytes, _native.TSB_D2H, copy_stream)
-            _native.stream_sync(local_rank, copy_stream)
+            async def e2e_step():
+                # (1) new weights arrive from the host
+                _native.memcpy_async(local_rank, src_flat.data_ptr(), host_src.data_ptr(), src_bytes, _native.TSB_H2D, copy_stream)
+                _native.stream_sync(local_rank, copy_stream)
+                # (2) publish + pull through the public API
+                await ts.put_state_dict(None, KEY, direct_rdma=True)
+                if n > 1:
+                    dist.barrier(device_ids=[local_rank])  # every source refreshed before anyone pulls
+                await ts.get_state_dict(KEY, user_state_dict=dst_sd, direct_rdma=True)
+                # (3) read the result sample back
+                _native.plan_run(sample_plan, copy_stream)
+                _native.memcpy_async(local_rank, sample_host.data_ptr(), sample_dev.data_ptr(), d2h_bytes, _native.TSB_D2H, copy_stream)
+                _native.stream_sync(local_rank, copy_stream)
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            await e2e_step()
-        barrier()
-        e_launch0 = _native.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            await e2e_step()
-        barrier()
-        e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
-        e2e_launches = int(allsum(_native.launch_count() - e_launch0))
-        assert torch.equal(sample_host.to(dev), sample_dev)
-        verify("e2e steps")
-        _native.plan_destroy(sample_plan)
+            for _ in range(max(1, min(args.warmup, 2))):
+                await e2e_step()
+            barrier()
+            e_launch0 = _native.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                await e2e_step()
+            barrier()
+            e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
+            e2e_launches = int(allsum(_native.launch_count() - e_launch0))
+            assert torch.equal(sample_host.to(dev), sample_dev)
+            verify("e2e steps")
+            _native.plan_destroy(sample_plan)
         return dict(first_ms=first_ms, dev_ms=dev_ms_max, wall_ms=wall_ms_max, kern_avg=kern_avg_max, info=info,
                     launches=total_launches, clocks=clocks, e2e_ms=e2e_ms, e2e_launches=e2e_launches,
                     h2d=int(allsum(src_bytes)), d2h=int(allsum(d2h_bytes)))
@@ -463,7 +488,7 @@ def run_ours(args):
         peaks, peak_src = load_peaks()
         steps = args.steps
         value = sd_bytes * steps / (r["dev_ms"] / 1e3) / 1e9
-        e2e = sd_bytes * steps / (r["e2e_ms"] / 1e3) / 1e9
+        e2e = sd_bytes * steps / (r["e2e_ms"] / 1e3) / 1e9 if r["e2e_ms"] else None
         info = r["info"]
         # per-launch algorithmic bytes on THIS rank: bytes read + bytes written (SURVEY section 8d:
         # HBM-bound points count 2 x payload); remote reads do not touch local HBM
@@ -516,7 +541,7 @@ def run_ours(args):
             },
             "clocks": r["clocks"],
             "e2e": {"value": e2e, "unit": "GB/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "ms_per_step": r["e2e_ms"] / steps, "gpu_launches": r["e2e_launches"]},
+                    "ms_per_step": (r["e2e_ms"] / steps) if r["e2e_ms"] else None, "gpu_launches": r["e2e_launches"]},
             "gpu_launches": r["launches"],
             "roofline": roofline,
             "nvlink_fraction": (info["remote_src_bytes"] / (r["dev_ms"] / steps / 1e3) / 1e9 / NVLINK_NOMINAL_GBPS) if n > 1 else 0.0,
@@ -543,6 +568,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -297,3 +297,16 @@ def test_scaled_llama_fsdp_to_tp_matches_oracle(n):
         assert info["payload_bytes"] == sum(v.numel() * 2 for v in dest_sd.values())
         assert info["src_bytes"] == info["payload_bytes"]  # no read amplification
         sync.close()
+
+
+def test_plan_rebuilt_when_destination_changes():
+    """A cached plan must never write tensors of a previous call (the reference's single cached plan
+    would; see state_dict_utils.py:198-201)."""
+    w = torch.randn(64, 64, device=DEV)
+    handles = DirectWeightSyncSource().register({"w": w}, rank=0)
+    sync = DirectWeightSyncDest()
+    d1 = torch.zeros(64, 64, device=DEV)
+    run(sync.pull({"w": [handles["w"]]}, {"w": d1}))
+    d2 = torch.zeros(64, 64, device=DEV)
+    run(sync.pull({"w": [handles["w"]]}, {"w": d2}))
+    assert torch.equal(d1, w) and torch.equal(d2, w)

@@ -214,7 +214,7 @@ def test_direct_rdma_state_dict_through_api():
         try:
             src = {"w": torch.randn(256, 128, device=DEV), "b": torch.randn(128, device=DEV)}
             await ts.put_state_dict(src, "policy", direct_rdma=True)
-            assert sorted(await ts.keys("policy")) == ["policy/num_ranks", "policy/rank_0"]
+            assert sorted(await ts.keys()) == ["policy/num_ranks", "policy/rank_0"]
             dst = {"w": torch.zeros(256, 128, device=DEV), "b": torch.zeros(128, device=DEV)}
             out = await ts.get_state_dict("policy", user_state_dict=dst, direct_rdma=True)
             assert out is dst and torch.equal(dst["w"], src["w"]) and torch.equal(dst["b"], src["b"])

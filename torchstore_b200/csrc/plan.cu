@@ -420,7 +420,7 @@ int tsb_plan_create(int device, const tsb_rect_t* rects, uint64_t n, uint32_t fl
   p->tile_units = tile_units;
   p->info = c.info;
   p->kind = c.kind();
-  const uint32_t per_sm = env_u32("TSB_CTAS_PER_SM", 4);
+  const uint32_t per_sm = env_u32("TSB_CTAS_PER_SM", 3);
   uint64_t grid = static_cast<uint64_t>(sm) * per_sm;
   if (grid > tiles.size()) grid = tiles.size();
   if (grid == 0) grid = 1;

@@ -290,6 +290,7 @@ class DirectWeightSyncDest:
 
     def __init__(self) -> None:
         self._plan: list[_TransferOp] | None = None
+        self._plan_signature: tuple | None = None
         self._native_plans: dict[int, int] = {}  # device -> plan id
         self.last_pull_ms: dict[int, float] = {}  # device -> kernel time of the last pull
 
@@ -357,6 +358,14 @@ class DirectWeightSyncDest:
             return src, dst_full
         return src_window.sub(op.src_slices), dst_full.sub(op.dest_slices)
 
+    @staticmethod
+    def _signature(dest_state_dict) -> tuple:
+        sig = []
+        for name, param in dest_state_dict.items():
+            local = getattr(param, "_local_tensor", param)
+            sig.append((name, local.data_ptr(), tuple(local.shape), local.dtype))
+        return tuple(sig)
+
     def _compile(self) -> None:
         per_device: dict[int, list] = defaultdict(list)
         for op in self._plan:
@@ -385,9 +394,15 @@ class DirectWeightSyncDest:
                    dest_slices: dict[str, TensorSlice] | None = None) -> None:
         """Pull every overlapping region into ``dest_state_dict`` (in place).  Returns when the
         bytes are in destination HBM (so the caller may tell the source it is done reading)."""
+        signature = self._signature(dest_state_dict)
+        if self._plan is not None and signature != self._plan_signature:
+            # same object asked to fill different memory: the cached plan would write the old tensors
+            logger.info("destination tensors changed; rebuilding the transfer plan")
+            self.close()
         if self._plan is None:
             self._plan = self._build_plan(all_handles, dest_state_dict, dest_slices)
             self._compile()
+            self._plan_signature = signature
         events = self.launch()
         for dev, (start, done) in events.items():
             await wait_event(done)

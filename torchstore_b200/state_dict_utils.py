@@ -30,7 +30,8 @@ class _DirectRDMACache:
     """Per-client state of direct weight sync (lazily created halves, published keys, handles)."""
 
     source: Any = None
-    dest: Any = None
+    dest: Any = None  # most recently used DirectWeightSyncDest (reference field)
+    dests: dict = field(default_factory=dict)  # key -> DirectWeightSyncDest (one cached plan per key)
     registered: set = field(default_factory=set)
     handles: dict = field(default_factory=dict)
 
@@ -47,8 +48,9 @@ def reset_direct_cache(store=None) -> None:
     keys = list(_rdma_cache) if store is None else [id(store)]
     for k in keys:
         cache = _rdma_cache.pop(k, None)
-        if cache is not None and cache.dest is not None:
-            cache.dest.close()
+        if cache is not None:
+            for d in cache.dests.values():
+                d.close()
 
 
 async def put_state_dict(store, state_dict, key, direct_rdma=False, transfer_dtype=None):
@@ -126,8 +128,10 @@ async def _get_state_dict_direct_rdma(store, key, user_state_dict):
     from torchstore_b200.direct_weight_sync import DirectWeightSyncDest
 
     cache = _get_rdma_cache(store)
-    if cache.dest is None:
-        cache.dest = DirectWeightSyncDest()
+    # one destination object (= one cached transfer plan) per state-dict key; the reference keeps a
+    # single one per client (state_dict_utils.py:198-201), which silently replays the first key's plan
+    # for every later key
+    cache.dest = cache.dests.setdefault(key, DirectWeightSyncDest())
     if key not in cache.handles:
         num_ranks = await store.get(f"{key}/num_ranks")
         all_handles = defaultdict(list)
@@ -135,4 +139,4 @@ async def _get_state_dict_direct_rdma(store, key, user_state_dict):
             for name, handle in (await store.get(f"{key}/rank_{r}")).items():
                 all_handles[name].append(handle)
         cache.handles[key] = all_handles
-    await cache.dest.pull(cache.handles[key], user_state_dict)
+    await cache.dests[key].pull(cache.handles[key], user_state_dict)
