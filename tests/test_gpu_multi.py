@@ -139,3 +139,32 @@ def test_two_process_ipc_direct_sync_and_store(same_gpu):
         mp.spawn(_ipc_worker, args=(world, port, d, same_gpu), nprocs=world, join=True)
         for r in range(world):
             assert np.load(os.path.join(d, f"{r}.npy")).all(), (r, np.load(os.path.join(d, f"{r}.npy")))
+
+
+@needs2
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.int32])
+def test_config2_flat_4gib_between_two_gpus(dtype):
+    """BASELINE config #2: direct_weight_sync of a 4 GiB flat tensor GPU0 -> GPU1, same placement
+    (one exact-match op); bf16 random weights and the int32 arange variant, bit-exact."""
+    from torchstore_b200.direct_weight_sync import DirectWeightSyncDest, DirectWeightSyncSource
+
+    nbytes = 4 << 30
+    n = nbytes // dtype.itemsize
+    if dtype == torch.int32:
+        src = torch.arange(n, dtype=torch.int32, device="cuda:0")
+    else:
+        src = torch.empty(n, dtype=dtype, device="cuda:0").normal_(0, 0.02)
+    handles = DirectWeightSyncSource().register({"flat": src}, rank=0)
+    dst = torch.zeros(n, dtype=dtype, device="cuda:1")
+    sync = DirectWeightSyncDest()
+    run(sync.pull({"flat": [handles["flat"]]}, {"flat": dst}))
+    assert len(sync._plan) == 1 and sync._plan[0].dest_tensor is None
+    a = src.view(torch.int32) if dtype == torch.int32 else src.view(torch.int16)
+    b = dst.view(torch.int32) if dtype == torch.int32 else dst.view(torch.int16)
+    assert int(a.to(torch.int64).sum()) == int(b.to(torch.int64).sum())  # checksum at full size
+    step = n // 64
+    for i in range(0, n, step):  # spot-check 64 windows bit for bit
+        assert torch.equal(src[i:i + 4096].cpu(), dst[i:i + 4096].cpu())
+    gbps = nbytes / sync.last_pull_ms[1] / 1e6
+    print(f"config2 {dtype}: {sync.last_pull_ms[1]:.3f} ms, {gbps:.1f} GB/s")
+    sync.close()

@@ -30,10 +30,10 @@ struct DeviceGuard {
   explicit DeviceGuard(int device) {
     err = cudaGetDevice(&prev);
     if (err != cudaSuccess) { ok = false; return; }
-    if (prev != device) {
-      err = cudaSetDevice(device);
-      if (err != cudaSuccess) ok = false;
-    }
+    // always set: on a thread that never touched CUDA (e.g. the actor-server thread) this is what
+    // binds the primary context, which the driver-API calls in runtime.cu rely on
+    err = cudaSetDevice(device);
+    if (err != cudaSuccess) ok = false;
     cur = device;
   }
   ~DeviceGuard() {
