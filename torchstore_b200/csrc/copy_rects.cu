@@ -316,40 +316,63 @@ __device__ __forceinline__ void stage_rect(DevRect* sdst, const DevRect* gsrc) {
 }
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Tile scheduling.  Every CTA owns the first three tiles of its column statically
+// (b, b+grid, b+2*grid: their headers can be prefetched at once); after that tiles are claimed
+// from a global atomic counter, so CTAs that happened to draw slow tiles (NVLink sources, short
+// remainders) simply claim fewer -- no tail imbalance when tile costs are heterogeneous.  The
+// claim for tile k+3 is issued before tile k's payload moves and only consumed after it, so the
+// atomic's round trip is never exposed.  The last CTA to finish resets the counters, which keeps a
+// sync at one kernel launch (a plan must not run concurrently with itself).
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 4) copy_rects_kernel(LaunchParams p) {
+__global__ void __launch_bounds__(kThreads, 3) copy_rects_kernel(LaunchParams p) {
   __shared__ DevRect srect[2];
-  const uint32_t stride = gridDim.x;
-  uint32_t t = blockIdx.x;
-  if (t >= p.num_tiles) return;
-
-  DevTile cur = p.tiles[t];
-  uint32_t tn = t + stride;
-  DevTile nxt = cur;
-  if (tn < p.num_tiles) nxt = p.tiles[tn];
-  stage_rect(&srect[0], &p.rects[cur.rect]);
-  stage_wait();
-  __syncthreads();
-
-  int buf = 0;
-  while (true) {
-    const bool has_next = tn < p.num_tiles;
-    const uint32_t tnn = tn + stride;
-    DevTile nn = nxt;
-    if (has_next) {
-      // header pipeline: rect of tile k+1 -> smem, tile entry k+2 -> registers, both in flight
-      // while tile k's payload moves
-      stage_rect(&srect[buf ^ 1], &p.rects[nxt.rect]);
-      if (tnn < p.num_tiles) nn = p.tiles[tnn];
-    }
-    process_tile<KIND>(srect[buf], cur.tile_in_rect, p.tile_units);
-    if (!has_next) break;
+  __shared__ uint32_t s_claim;
+  const uint32_t grid = gridDim.x;
+  const uint32_t n = p.num_tiles;
+  const bool dynamic = p.sched != nullptr;
+  uint32_t i0 = blockIdx.x;          // index (into p.tiles) of the current tile
+  uint32_t i1 = i0 + grid;           // next
+  uint32_t i2 = i1 + grid;           // the one after
+  if (i0 < n) {
+    DevTile cur = p.tiles[i0];
+    DevTile nxt = cur;
+    if (i1 < n) nxt = p.tiles[i1];
+    stage_rect(&srect[0], &p.rects[cur.rect]);
     stage_wait();
     __syncthreads();
-    cur = nxt;
-    nxt = nn;
-    tn = tnn;
-    buf ^= 1;
+
+    int buf = 0;
+    while (true) {
+      const bool has_next = i1 < n;
+      DevTile nn = nxt;
+      uint32_t claimed = i2 + grid;  // static fallback: keep striding
+      if (has_next) {
+        // header pipeline: rect of tile k+1 -> smem, tile entry k+2 -> registers, claim of tile
+        // k+3 -> in flight, all while tile k's payload moves
+        stage_rect(&srect[buf ^ 1], &p.rects[nxt.rect]);
+        if (i2 < n) nn = p.tiles[i2];
+        if (dynamic && threadIdx.x == 0) claimed = atomicAdd(p.sched, 1u) + 3u * grid;
+      }
+      process_tile<KIND>(srect[buf], cur.tile_in_rect, p.tile_units);
+      if (!has_next) break;
+      if (dynamic && threadIdx.x == 0) s_claim = claimed;
+      stage_wait();
+      __syncthreads();
+      if (dynamic) claimed = s_claim;
+      cur = nxt;
+      nxt = nn;
+      i1 = i2;
+      i2 = claimed;
+      buf ^= 1;
+    }
+  }
+  if (dynamic && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.sched + 1, 1u) == grid - 1) {  // last CTA out: re-arm for the next launch
+      p.sched[0] = 0;
+      p.sched[1] = 0;
+      __threadfence();
+    }
   }
 }
 
@@ -358,6 +381,19 @@ std::atomic<uint64_t> g_launches{0};
 }  // namespace
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int max_ctas_per_sm(uint32_t kind, int* out) {
+  int n = 0;
+  cudaError_t e;
+  switch (kind) {
+    case KIND_B16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, copy_rects_kernel<KIND_B16>, kThreads, 0); break;
+    case KIND_F32_BF16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, copy_rects_kernel<KIND_F32_BF16>, kThreads, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, copy_rects_kernel<KIND_GENERIC>, kThreads, 0); break;
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+  *out = n;
+  return TSB_OK;
+}
 
 int launch_copy_rects(const LaunchParams& p, uint32_t grid, uint32_t block, cudaStream_t stream) {
   if (p.num_tiles == 0) return TSB_OK;

@@ -26,6 +26,7 @@ struct Plan {
   int device = 0;
   DevTile* d_tiles = nullptr;
   DevRect* d_rects = nullptr;
+  uint32_t* d_sched = nullptr;
   uint32_t num_tiles = 0;
   uint32_t tile_units = 0;
   uint32_t kind = KIND_GENERIC;
@@ -334,6 +335,7 @@ void reap_pending_locked(PlanRegistry& reg, bool block) {
       DeviceGuard guard(pl->device);
       cudaFree(pl->d_tiles);
       cudaFree(pl->d_rects);
+      cudaFree(pl->d_sched);
       delete pl;
       reg.plans.erase(it);
     }
@@ -353,6 +355,7 @@ int plans_shutdown() {
     DeviceGuard guard(kv.second->device);
     cudaFree(kv.second->d_tiles);
     cudaFree(kv.second->d_rects);
+    cudaFree(kv.second->d_sched);
     delete kv.second;
   }
   reg.plans.clear();
@@ -420,7 +423,15 @@ int tsb_plan_create(int device, const tsb_rect_t* rects, uint64_t n, uint32_t fl
   p->tile_units = tile_units;
   p->info = c.info;
   p->kind = c.kind();
-  const uint32_t per_sm = env_u32("TSB_CTAS_PER_SM", 3);
+  uint32_t per_sm = env_u32("TSB_CTAS_PER_SM", 3);
+  {
+    // persistent kernel: never ask for more CTAs than can be co-resident
+    DeviceGuard guard(device);
+    int resident = 0;
+    if (guard.ok && max_ctas_per_sm(p->kind, &resident) == TSB_OK && resident > 0 &&
+        per_sm > static_cast<uint32_t>(resident))
+      per_sm = static_cast<uint32_t>(resident);
+  }
   uint64_t grid = static_cast<uint64_t>(sm) * per_sm;
   if (grid > tiles.size()) grid = tiles.size();
   if (grid == 0) grid = 1;
@@ -430,11 +441,14 @@ int tsb_plan_create(int device, const tsb_rect_t* rects, uint64_t n, uint32_t fl
     if (!guard.ok) { delete p; return cuda_fail(guard.err, "cudaSetDevice"); }
     cudaError_t e = cudaMalloc(&p->d_tiles, tiles.size() * sizeof(DevTile));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_rects, c.rects.size() * sizeof(DevRect));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_sched, 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(p->d_sched, 0, 2 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tiles, tiles.data(), tiles.size() * sizeof(DevTile), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_rects, c.rects.data(), c.rects.size() * sizeof(DevRect), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       cudaFree(p->d_tiles);
       cudaFree(p->d_rects);
+      cudaFree(p->d_sched);
       delete p;
       return cuda_fail(e, "plan upload");
     }
@@ -473,7 +487,8 @@ int tsb_plan_run(tsb_plan_t plan, void* stream) {
   if (!guard.ok) return cuda_fail(guard.err, "cudaSetDevice");
   uint32_t kind = p->kind;
   if (getenv("TSB_FORCE_GENERIC")) kind = KIND_GENERIC;
-  LaunchParams lp{p->d_tiles, p->d_rects, p->num_tiles, p->tile_units, kind};
+  uint32_t* sched = getenv("TSB_STATIC_SCHED") ? nullptr : p->d_sched;
+  LaunchParams lp{p->d_tiles, p->d_rects, p->num_tiles, p->tile_units, kind, sched};
   return launch_copy_rects(lp, p->info.grid, p->info.block, s);
 }
 
@@ -488,6 +503,7 @@ int tsb_plan_destroy(tsb_plan_t plan) {
   // cudaFree synchronises with outstanding work that uses the buffers
   cudaFree(p->d_tiles);
   cudaFree(p->d_rects);
+  cudaFree(p->d_sched);
   delete p;
   return TSB_OK;
 }

@@ -109,10 +109,12 @@ struct LaunchParams {
   uint32_t num_tiles;
   uint32_t tile_units;
   uint32_t kind;
+  uint32_t* sched;  // {claim counter, finished-CTA counter}; nullptr = fully static striding
 };
 
 // defined in copy_rects.cu
 int launch_copy_rects(const LaunchParams& p, uint32_t grid, uint32_t block, cudaStream_t stream);
 void count_launch();
+int max_ctas_per_sm(uint32_t kind, int* out);
 
 }  // namespace tsb
