@@ -128,3 +128,24 @@ def test_unsupported_cast_is_rejected():
     b = torch.zeros(8, dtype=torch.float32)
     with pytest.raises(NotImplementedError):
         build_rects([(StridedMem.from_tensor(a), StridedMem.from_tensor(b))])
+
+
+def test_unequal_sources_are_spread_proportionally():
+    """A small remote share must be spread over the whole launch, not bunched at the front."""
+    from torchstore_b200.planner import StridedMem, build_rects
+
+    big = torch.zeros(5 * 64 * 1024, dtype=torch.int32)   # local: 5x the tiles
+    small = torch.zeros(64 * 1024, dtype=torch.int32)     # remote
+    out_b, out_s = torch.zeros_like(big), torch.zeros_like(small)
+    sb = StridedMem.from_tensor(big)
+    ss = StridedMem.from_tensor(small)
+    pairs = [(StridedMem(sb.ptr, sb.shape, sb.stride, sb.dtype, device=0), StridedMem.from_tensor(out_b)),
+             (StridedMem(ss.ptr, ss.shape, ss.stride, ss.dtype, device=1), StridedMem.from_tensor(out_s))]
+    rects, n = build_rects(pairs)
+    _, tiles, info = _native.plan_compile_host(0, rects, n, 0, 256)
+    order = tiles[:, 0]
+    assert (order == 1).sum() == 64 and (order == 0).sum() == 320
+    pos = np.nonzero(order == 1)[0]
+    gaps = np.diff(pos)
+    assert gaps.min() >= 5 and gaps.max() <= 7  # one remote tile every ~6 tiles, start to finish
+    assert pos[0] <= 6 and pos[-1] >= len(order) - 7

@@ -270,18 +270,32 @@ struct Compiler {
       return rot(a) < rot(b);
     });
     for (int32_t k : keys) cursors.push_back({&by_src[k]});
-    size_t live = cursors.size();
-    while (live) {
-      live = 0;
-      for (Cursor& c : cursors) {
-        while (c.ri < c.rect_ids->size() && c.ti >= rect_tiles[(*c.rect_ids)[c.ri]]) {
-          ++c.ri;
-          c.ti = 0;
-        }
-        if (c.ri >= c.rect_ids->size()) continue;
-        out->push_back({(*c.rect_ids)[c.ri], c.ti++});
-        ++live;
+    // Proportional interleave: group g's j-th tile sits at fractional position (j + 0.5) / n_g of the
+    // launch, so every source is drained at a constant rate for the whole kernel.  With equal groups
+    // (FSDP(N)->TP(N)) this is plain round-robin; with unequal ones (mostly-local plans) it keeps the
+    // small NVLink share spread out instead of bunching it at the front, where strict alternation
+    // would throttle the local copies to the link rate.
+    std::vector<uint64_t> group_tiles(cursors.size(), 0);
+    for (size_t g = 0; g < cursors.size(); ++g)
+      for (uint32_t rid : *cursors[g].rect_ids) group_tiles[g] += rect_tiles[rid];
+    std::vector<uint64_t> emitted(cursors.size(), 0);
+    for (uint64_t k = 0; k < total; ++k) {
+      size_t best = cursors.size();
+      // pick the group that is furthest behind its schedule: minimise (2*emitted+1)/(2*n)
+      for (size_t g = 0; g < cursors.size(); ++g) {
+        if (emitted[g] >= group_tiles[g]) continue;
+        if (best == cursors.size()) { best = g; continue; }
+        const unsigned __int128 lhs = static_cast<unsigned __int128>(2 * emitted[g] + 1) * group_tiles[best];
+        const unsigned __int128 rhs = static_cast<unsigned __int128>(2 * emitted[best] + 1) * group_tiles[g];
+        if (lhs < rhs) best = g;
       }
+      Cursor& c = cursors[best];
+      while (c.ti >= rect_tiles[(*c.rect_ids)[c.ri]]) {
+        ++c.ri;
+        c.ti = 0;
+      }
+      out->push_back({(*c.rect_ids)[c.ri], c.ti++});
+      ++emitted[best];
     }
   }
 };
