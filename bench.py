@@ -282,6 +282,8 @@ def run_ours(args):
     os.environ.setdefault("LOCAL_WORLD_SIZE", str(world))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if not os.environ.get("TSB_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; keep stdout to ONE JSON line
     dist.init_process_group("nccl", device_id=dev)
     _native.init()
     n = world
