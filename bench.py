@@ -269,9 +269,21 @@ def run_ours(args):
     from torchstore_b200 import _native
     from torchstore_b200.planner import StridedMem, build_rects
 
+    import faulthandler
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # a hung collective / RPC must leave evidence: dump every thread's stack to stderr after the
+    # watchdog period, repeatedly
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(int(os.environ.get("TSB_BENCH_WATCHDOG_S", "90")), repeat=True, file=sys.stderr)
+    t_start = time.perf_counter()
+
+    def phase(msg):
+        if os.environ.get("TSB_BENCH_VERBOSE", "1") == "1":
+            print(f"[bench r{rank} +{time.perf_counter() - t_start:7.2f}s] {msg}", file=sys.stderr, flush=True)
+
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -284,9 +296,11 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if not os.environ.get("TSB_KEEP_NCCL_DEBUG"):
         os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; keep stdout to ONE JSON line
+    phase("init_process_group")
     dist.init_process_group("nccl", device_id=dev)
     _native.init()
     n = world
+    phase("generating weights")
 
     layout = workloads.llama_layout(workloads.LLAMA3_8B)
     sd_bytes = workloads.state_dict_bytes(layout)
@@ -320,6 +334,7 @@ def run_ours(args):
         do += (nd + 63) // 64 * 64
         del full, want
     torch.cuda.synchronize()
+    phase("weights ready")
 
     # ---- state dicts as the API sees them: DTensors on a 1-D mesh (plain tensors at N == 1) -------
     if n > 1:
@@ -362,11 +377,14 @@ def run_ours(args):
             await ts.initialize_spmd(ts.LocalRankStrategy(), rendezvous=dist.distributed_c10d._get_default_store())
         else:
             await ts.initialize()
+        phase("store initialized")
         # first sync: registers handles, exchanges them through the store, builds + caches the plan
         t_first = time.perf_counter()
         await ts.put_state_dict(src_sd, KEY, direct_rdma=True)
+        phase("handles published")
         barrier()
         await ts.get_state_dict(KEY, user_state_dict=dst_sd, direct_rdma=True)
+        phase("first pull done")
         barrier()
         first_ms = (time.perf_counter() - t_first) * 1e3
 
@@ -377,6 +395,7 @@ def run_ours(args):
                 raise SystemExit(f"[rank {rank}] PARITY FAILURE after {tag}: {bad[:5]} ({len(bad)} tensors)")
 
         verify("first sync")
+        phase("first sync verified")
         from torchstore_b200.state_dict_utils import _get_rdma_cache
 
         cl = await ts.client()
@@ -417,6 +436,7 @@ def run_ours(args):
         if args.profiler_range:
             torch.cuda.cudart().cudaProfilerStop()
         dev_ms = ev0.elapsed_ms(ev1)
+        phase(f"timed steps done: {dev_ms / args.steps:.3f} ms/step on this rank")
         barrier()
         launches = _native.launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
@@ -471,6 +491,7 @@ def run_ours(args):
             for _ in range(args.steps):
                 await e2e_step()
             barrier()
+            phase("e2e steps done")
             e2e_ms = allmax((time.perf_counter() - t0) * 1e3)
             e2e_launches = int(allsum(_native.launch_count() - e_launch0))
             assert torch.equal(sample_host.to(dev), sample_dev)
@@ -481,6 +502,7 @@ def run_ours(args):
                     h2d=int(allsum(src_bytes)), d2h=int(allsum(d2h_bytes)))
 
     r = asyncio.run(main())
+    faulthandler.cancel_dump_traceback_later()
 
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
