@@ -278,6 +278,17 @@ def run_ours(args):
     # watchdog period, repeatedly
     faulthandler.enable()
     faulthandler.dump_traceback_later(int(os.environ.get("TSB_BENCH_WATCHDOG_S", "90")), repeat=True, file=sys.stderr)
+    # ... and must not hang the caller forever: hard deadline for the whole run
+    deadline = float(os.environ.get("TSB_BENCH_DEADLINE_S", "420"))
+
+    def _deadline():
+        print(f"[bench r{os.environ.get('RANK', '0')}] deadline of {deadline:.0f}s exceeded; aborting", file=sys.stderr, flush=True)
+        faulthandler.dump_traceback(file=sys.stderr)
+        os._exit(3)
+
+    _timer = threading.Timer(deadline, _deadline)
+    _timer.daemon = True
+    _timer.start()
     t_start = time.perf_counter()
 
     def phase(msg):
@@ -503,6 +514,7 @@ def run_ours(args):
 
     r = asyncio.run(main())
     faulthandler.cancel_dump_traceback_later()
+    _timer.cancel()
 
     cpu = None
     if rank == 0 and n == 1 and not args.no_cpu_baseline:

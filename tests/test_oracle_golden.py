@@ -203,12 +203,6 @@ def _cast_vectors():
     return np.load(os.path.join(GOLDEN, "cast_vectors.npz"))
 
 
-def nan_mask(bits: np.ndarray) -> np.ndarray:
-    """NaN positions of an array of IEEE bit patterns (uint16 is ambiguous: pass kind via dtype
-    wrappers below)."""
-    raise NotImplementedError
-
-
 def _nan16(bits, exp_mask, man_mask):
     return ((bits & exp_mask) == exp_mask) & ((bits & man_mask) != 0)
 
