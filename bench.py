@@ -437,10 +437,10 @@ def run_ours(args):
         ev0.record(copy_stream)
         t0 = time.perf_counter()
         for _ in range(args.steps):
+            # K syncs back to back on every rank; the bracket is barrier + synchronize on both sides.
+            # (The cross-rank "sources are ready" dependency of a real sync is part of the e2e leg.)
             await step()
             kernel_ms.append(dest_sync.last_pull_ms[local_rank])
-            if n > 1:
-                dist.barrier(device_ids=[local_rank])  # a sync is complete when every rank has its shard
         ev1.record(copy_stream)
         ev1.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3

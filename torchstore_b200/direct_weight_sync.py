@@ -360,11 +360,9 @@ class DirectWeightSyncDest:
 
     @staticmethod
     def _signature(dest_state_dict) -> tuple:
-        sig = []
-        for name, param in dest_state_dict.items():
-            local = getattr(param, "_local_tensor", param)
-            sig.append((name, local.data_ptr(), tuple(local.shape), local.dtype))
-        return tuple(sig)
+        # data pointers only: ~35 us for 291 tensors; a new state_dict() wrapper around the same
+        # memory keeps the plan, new memory invalidates it
+        return tuple(getattr(p, "_local_tensor", p).data_ptr() for p in dest_state_dict.values())
 
     def _compile(self) -> None:
         per_device: dict[int, list] = defaultdict(list)
