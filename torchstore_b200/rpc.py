@@ -116,8 +116,12 @@ class LocalActorRef:
 
 
 def _resolve_ref(address, authkey, name, pid):
+    """Unpickle a handle: inside the owning process it becomes a direct (in-thread) reference."""
     if pid == os.getpid():
         return LocalActorRef(name)
+    server = ActorServer.instance(create=False)
+    if server is not None and tuple(server.address) == tuple(address) and server.authkey == authkey:
+        return LocalActorRef(name)  # a handle that travelled through another process and came home
     return RemoteActorRef(address, authkey, name)
 
 
@@ -192,7 +196,9 @@ class ActorServer:
 
     def __init__(self, host: str = "127.0.0.1"):
         self.authkey = os.urandom(16)
-        self._listener = Listener((host, 0), authkey=self.authkey)
+        # backlog: every rank of the box may connect at the same instant (multiprocessing's default
+        # of 1 overflows the accept queue at 8 ranks and a dropped handshake hangs the client forever)
+        self._listener = Listener((host, 0), backlog=512, authkey=self.authkey)
         self.address = self._listener.address
         self._loop = asyncio.new_event_loop()
         self._closed = False
