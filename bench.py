@@ -124,8 +124,27 @@ class ClockSampler:
                 "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
+_REAL_STDOUT_FD = None
+
+
+def capture_stdout():
+    """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr, so that
+    stdout carries exactly ONE line: the JSON result written by emit()."""
+    global _REAL_STDOUT_FD
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.flush()
+        _REAL_STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
 def emit(obj):
-    print(json.dumps(obj), flush=True)
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT_FD, line)
 
 
 # =================================================================================================
@@ -600,7 +619,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -609,6 +628,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-input leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -30,6 +30,7 @@ from __future__ import annotations
 import asyncio
 import logging
 import os
+import time
 from collections import defaultdict
 from dataclasses import dataclass
 
@@ -51,6 +52,7 @@ async def wait_event(event: "_native.Event") -> None:
     spins = 0
     while not event.query():
         spins += 1
+        time.sleep(0)  # hand the GIL to other threads (actor server, samplers) between polls
         await asyncio.sleep(0 if spins < 2000 else 0.0002)
 
 
