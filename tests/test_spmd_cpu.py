@@ -50,6 +50,15 @@ def _worker(rank, world, port, outdir):
         res["exists_missing"] = await ts.exists("nope")
         dist.barrier()
         await ts.shutdown()
+        # the same job can bring the store up again: nothing of the first incarnation leaks in
+        await ts.initialize_spmd(ts.LocalRankStrategy())
+        res["second_keys"] = await ts.keys()
+        dist.barrier()
+        await ts.put(f"again_{rank}", rank)
+        dist.barrier()
+        res["second_peer"] = await ts.get(f"again_{(rank + 1) % world}")
+        dist.barrier()
+        await ts.shutdown()
         dist.destroy_process_group()
         with open(os.path.join(outdir, f"{rank}.json"), "w") as f:
             json.dump(res, f)
@@ -70,6 +79,7 @@ def test_two_rank_spmd_store_on_cpu():
         assert out[r]["my_volume"] == [str(r)]
         assert out[r]["sd"] == {"step": 11, "cfg": {"a": 1}}
         assert out[r]["exists_missing"] is False
+        assert out[r]["second_keys"] == [] and out[r]["second_peer"] == other
 
 
 def test_spmd_env_parsing(monkeypatch):

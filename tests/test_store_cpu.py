@@ -186,3 +186,66 @@ def test_request_from_any_rules():
     assert m.tensor_val is None and m.key == "k"
     a = TensorSlice((0, 0), [0], (8, 8), (2, 2), (1,))
     assert isinstance(a.coordinates, tuple) and hash(a) == hash(TensorSlice((0, 0), (0,), (8, 8), (2, 2), (1,)))
+
+
+def test_host_strategy_single_volume(monkeypatch):
+    monkeypatch.setenv("HOSTNAME", "box-a")
+
+    async def main():
+        await ts.initialize(num_storage_volumes=1, strategy=ts.HostStrategy())
+        try:
+            await ts.put("k", [1, 2, 3])
+            assert await ts.get("k") == [1, 2, 3]
+            c = await ts.client()
+            vm = await c._controller.locate_volumes.call_one(["k"])
+            assert list(vm["k"].keys()) == ["box-a"]
+            monkeypatch.setenv("HOSTNAME", "box-b")  # a client on another host has no volume here
+            with pytest.raises(KeyError, match="No corresponding storage volume"):
+                await ts.put("k2", 1)
+        finally:
+            await ts.shutdown()
+
+    run(main())
+
+
+def test_rpc_errors_and_mesh():
+    from torchstore_b200 import rpc
+
+    class Thing(rpc.Actor):
+        def __init__(self, n):
+            self.n = n
+
+        @rpc.endpoint
+        async def add(self, x):
+            return self.n + x
+
+        @rpc.endpoint
+        async def boom(self):
+            raise KeyError("nope")
+
+        async def hidden(self):
+            return 1
+
+    async def main():
+        a = rpc.register_actor("t/a", Thing(1))
+        b = rpc.register_actor("t/b", Thing(10))
+        try:
+            assert await a.add.call_one(2) == 3
+            with pytest.raises(rpc.ActorError, match="KeyError"):
+                await a.boom.call_one()
+            with pytest.raises(rpc.ActorError, match="not an endpoint"):
+                await a.hidden.call_one()
+            mesh = rpc.ActorMesh([({"gpus": 0}, a), ({"gpus": 1}, b)])
+            assert await mesh.add.call(5) == [({"gpus": 0}, 6), ({"gpus": 1}, 15)]
+            assert await mesh.slice(gpus=1).add.call_one(1) == 11
+            with pytest.raises(KeyError):
+                mesh.slice(gpus=7)
+            with pytest.raises(rpc.ActorError, match="more than one"):
+                await mesh.add.call_one(1)
+        finally:
+            rpc.unregister_actor("t/a")
+            rpc.unregister_actor("t/b")
+        with pytest.raises(rpc.ActorError, match="no actor named"):
+            await a.add.call_one(1)
+
+    run(main())

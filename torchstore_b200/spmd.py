@@ -29,8 +29,9 @@ from torchstore_b200.strategy import HostStrategy, LocalRankStrategy, TorchStore
 logger = logging.getLogger(__name__)
 
 
-def _spmd_key(store_name: str, suffix: str) -> str:
-    return f"torchstore/spmd/{store_name}/{suffix}"
+def _spmd_key(store_name: str, suffix: str, generation: int | None = None) -> str:
+    gen = "" if generation is None else f"g{generation}/"
+    return f"torchstore/spmd/{store_name}/{gen}{suffix}"
 
 
 @dataclass(frozen=True)
@@ -74,7 +75,8 @@ class _SPMDSession:
     """Per-process resources of an SPMD store; ``rendezvous`` is reusable by callers."""
 
     def __init__(self, *, rendezvous, controller, store_name: str, is_primary: bool, env: SPMDEnv,
-                 owned_actors: list[str]) -> None:
+                 owned_actors: list[str], generation: int = 1) -> None:
+        self.generation = generation
         self.rendezvous = rendezvous
         self.controller = controller
         self.is_primary = is_primary
@@ -88,9 +90,10 @@ class _SPMDSession:
         if _api._spmd_state_map.pop(self._store_name, None) is None:
             return
         name = self._store_name
+        gen = self.generation
         err: Exception | None = None
         try:
-            self.rendezvous.add(_spmd_key(name, "shutdown_arrivals"), 1)
+            self.rendezvous.add(_spmd_key(name, "shutdown_arrivals", gen), 1)
             if self.is_primary:
                 status = "ok"
                 try:
@@ -98,17 +101,17 @@ class _SPMDSession:
                     import time
 
                     deadline = time.time() + 120
-                    while self.rendezvous.add(_spmd_key(name, "shutdown_arrivals"), 0) < self.env.world_size:
+                    while self.rendezvous.add(_spmd_key(name, "shutdown_arrivals", gen), 0) < self.env.world_size:
                         if time.time() > deadline:
                             raise RuntimeError("Timed out waiting for all ranks to reach shutdown")
                         time.sleep(0.002)
                     await self.controller.teardown.call()
                 except Exception as e:  # noqa: BLE001
                     err, status = e, repr(e)
-                self.rendezvous.set(_spmd_key(name, "shutdown"), status)
+                self.rendezvous.set(_spmd_key(name, "shutdown", gen), status)
             else:
                 try:
-                    status = self.rendezvous.get(_spmd_key(name, "shutdown")).decode()
+                    status = self.rendezvous.get(_spmd_key(name, "shutdown", gen)).decode()
                 except Exception as e:
                     raise RuntimeError("Timed out waiting for TorchStore shutdown") from e
                 if status != "ok":
@@ -157,6 +160,9 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
     if rendezvous is None:
         rendezvous = _open_rendezvous(env, rendezvous_timeout)
 
+    # k-th initialisation of this store name in this job: every rank bumps its own counter, so all
+    # ranks derive the same generation and never read keys of an earlier incarnation
+    gen = int(rendezvous.add(_spmd_key(store_name, f"generation/{env.rank}"), 1))
     server = rpc.ActorServer.instance()
     owned: list[str] = []
     hosts_volume = isinstance(strategy, LocalRankStrategy) or env.local_rank == 0
@@ -165,21 +171,21 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
         device = env.local_rank if torch.cuda.is_available() else None
         vol = StorageVolume(id_func=strategy.get_volume_id, device=device)
         strategy_mod._spawn_rank[0] = 0
-        vol_name = f"{store_name}/volume/{env.rank}"
+        vol_name = f"{store_name}/g{gen}/volume/{env.rank}"
         owned.append(vol_name)
         vol_ref = rpc.register_actor(vol_name, vol)
-        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}"), pickle.dumps(vol_ref))
+        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}", gen), pickle.dumps(vol_ref))
     else:
-        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}"), pickle.dumps(None))
+        rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}", gen), pickle.dumps(None))
 
-    controller_key = _spmd_key(store_name, "controller")
+    controller_key = _spmd_key(store_name, "controller", gen)
     if env.rank == 0:
         members = []
         for r in range(env.world_size):
-            ref = pickle.loads(rendezvous.get(_spmd_key(store_name, f"volume/{r}")))
+            ref = pickle.loads(rendezvous.get(_spmd_key(store_name, f"volume/{r}", gen)))
             if ref is not None:
                 members.append(({"gpus": r}, ref))
-        name = f"{store_name}/controller"
+        name = f"{store_name}/g{gen}/controller"
         owned.append(name)
         controller = rpc.register_actor(name, Controller())
         await controller.init.call(strategy=strategy, num_storage_volumes=len(members),
@@ -189,7 +195,7 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
         controller = pickle.loads(rendezvous.get(controller_key))
     del server
     _api._spmd_state_map[store_name] = _SPMDSession(rendezvous=rendezvous, controller=controller, store_name=store_name,
-                                                   is_primary=(env.rank == 0), env=env, owned_actors=owned)
+                                                   is_primary=(env.rank == 0), env=env, owned_actors=owned, generation=gen)
 
 
 __all__ = ["SPMDEnv", "initialize"]
