@@ -159,8 +159,6 @@ def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 2
 
     The workload is a bounded SAMPLE of the Llama-3-8B FSDP(n)->TP(n) sync: the first L transformer
     layers, all n source and n destination ranks emulated in one address space, L sized to the budget."""
-    import ctypes as C
-
     import numpy as np
 
     from oracle import c_oracle
@@ -225,15 +223,12 @@ def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 2
 
     for _ in range(max(1, warmup)):
         one_sync()
-    # parity of the port itself: every destination equals the matching slice of the sources
-    name0 = next(iter(layout))
     t0 = time.perf_counter()
     done = 0
     while done < steps and (time.perf_counter() - t0 < budget_s or done == 0):
         one_sync()
         done += 1
     elapsed = time.perf_counter() - t0
-    del name0
     gbps = sample_bytes * done / elapsed / 1e9
     return {
         "value": gbps,
