@@ -68,7 +68,7 @@ def _free_port():
     return p
 
 
-def _ipc_worker(rank, world, port, outdir, same_gpu):
+def _ipc_worker(rank, world, port, pg_port, outdir, same_gpu):
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(0 if same_gpu else rank), "WORLD_SIZE": str(world),
                        "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
     os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
@@ -80,7 +80,7 @@ def _ipc_worker(rank, world, port, outdir, same_gpu):
     torch.cuda.set_device(dev)
 
     async def main():
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port + 1}", rank=rank, world_size=world)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{pg_port}", rank=rank, world_size=world)
         await ts.initialize_spmd(ts.LocalRankStrategy())
         # every rank owns rows [rank*R, (rank+1)*R) of a [world*R, C] weight (FSDP Shard(0)) and
         # wants columns [rank*C/world, ...) of all rows (TP Shard(1))
@@ -134,9 +134,9 @@ def test_two_process_ipc_direct_sync_and_store(same_gpu):
     if not same_gpu and _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
-    port = _free_port()
+    port, pg_port = _free_port(), _free_port()
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_ipc_worker, args=(world, port, d, same_gpu), nprocs=world, join=True)
+        mp.spawn(_ipc_worker, args=(world, port, pg_port, d, same_gpu), nprocs=world, join=True)
         for r in range(world):
             assert np.load(os.path.join(d, f"{r}.npy")).all(), (r, np.load(os.path.join(d, f"{r}.npy")))
 

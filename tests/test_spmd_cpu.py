@@ -22,7 +22,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, outdir):
+def _worker(rank, world, port, pg_port, outdir):
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
                        "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
     os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
@@ -31,7 +31,7 @@ def _worker(rank, world, port, outdir):
     import torchstore_b200 as ts
 
     async def main():
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port + 1}", rank=rank, world_size=world)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{pg_port}", rank=rank, world_size=world)
         await ts.initialize_spmd(ts.LocalRankStrategy())
         res = {}
         await ts.put(f"from_{rank}", {"rank": rank, "payload": list(range(rank + 3))})
@@ -68,9 +68,9 @@ def _worker(rank, world, port, outdir):
 
 def test_two_rank_spmd_store_on_cpu():
     world = 2
-    port = _free_port()
+    port, pg_port = _free_port(), _free_port()
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, port, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, pg_port, d), nprocs=world, join=True)
         out = [json.load(open(os.path.join(d, f"{r}.json"))) for r in range(world)]
     for r in range(world):
         other = (r + 1) % world

@@ -29,7 +29,8 @@ logger = getLogger(__name__)
 class _DirectRDMACache:
     """Per-client state of direct weight sync (lazily created halves, published keys, handles)."""
 
-    source: Any = None
+    source: Any = None  # most recently used DirectWeightSyncSource (reference field)
+    sources: dict = field(default_factory=dict)  # key -> DirectWeightSyncSource (handles + staging per key)
     dest: Any = None  # most recently used DirectWeightSyncDest (reference field)
     dests: dict = field(default_factory=dict)  # key -> DirectWeightSyncDest (one cached plan per key)
     registered: set = field(default_factory=set)
@@ -51,6 +52,8 @@ def reset_direct_cache(store=None) -> None:
         if cache is not None:
             for d in cache.dests.values():
                 d.close()
+            for src in cache.sources.values():
+                src._drop_plans()
 
 
 async def put_state_dict(store, state_dict, key, direct_rdma=False, transfer_dtype=None):
@@ -109,8 +112,9 @@ async def _put_state_dict_direct_rdma(store, state_dict, key, transfer_dtype=Non
     from torchstore_b200.direct_weight_sync import DirectWeightSyncSource
 
     cache = _get_rdma_cache(store)
-    if cache.source is None:
-        cache.source = DirectWeightSyncSource()
+    # one source object per key: the reference keeps a single one per client, whose handles and
+    # staging buffers are overwritten when a second key is registered (state_dict_utils.py:171-178)
+    cache.source = cache.sources.setdefault(key, DirectWeightSyncSource())
     if key not in cache.registered:
         assert state_dict is not None, "state_dict is required on first put_state_dict call with direct_rdma=True"
         rank, world_size = dist.get_rank(), dist.get_world_size()
@@ -124,7 +128,43 @@ async def _put_state_dict_direct_rdma(store, state_dict, key, transfer_dtype=Non
         cache.source.fence()
 
 
+def _try_all_gather(cache: _DirectRDMACache, key: str, user_state_dict) -> bool:
+    """Route "every rank reads every tensor in full from the ranks' own Shard(0) shards" to NCCL's
+    all-gather (collectives.py).  All ranks must agree, so the local verdict is min-reduced first."""
+    from torch.distributed.tensor import DTensor
+
+    from torchstore_b200.collectives import all_gather_state_dict, is_allgather_shaped
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return False
+    rank, world = dist.get_rank(), dist.get_world_size()
+    source = cache.sources.get(key)
+    ok = source is not None and key in cache.registered and bool(source._handles)
+    shards, dests = {}, {}
+    if ok:
+        ok = not any(isinstance(t, DTensor) for t in user_state_dict.values())
+    if ok:
+        slices = {n: h.tensor_slice for n, h in source._handles.items()}
+        ok = is_allgather_shaped(slices, {n: tuple(t.shape) for n, t in user_state_dict.items()}, rank, world)
+    if ok:
+        for n, h in source._handles.items():
+            shard = h.rdma_buffer._keepalive
+            dest = user_state_dict[n]
+            if shard is None or shard.dtype != dest.dtype or not dest.is_contiguous():
+                ok = False
+                break
+            shards[n], dests[n] = shard, dest
+    device = next(iter(user_state_dict.values())).device if user_state_dict else torch.device("cpu")
+    verdict = torch.tensor([1 if ok else 0], device=device if device.type == "cuda" else "cpu")
+    dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+    if int(verdict.item()) == 0:
+        return False
+    all_gather_state_dict(shards, dests)
+    return True
+
+
 async def _get_state_dict_direct_rdma(store, key, user_state_dict):
+    from torchstore_b200.collectives import allgather_enabled
     from torchstore_b200.direct_weight_sync import DirectWeightSyncDest
 
     cache = _get_rdma_cache(store)
@@ -132,6 +172,8 @@ async def _get_state_dict_direct_rdma(store, key, user_state_dict):
     # single one per client (state_dict_utils.py:198-201), which silently replays the first key's plan
     # for every later key
     cache.dest = cache.dests.setdefault(key, DirectWeightSyncDest())
+    if allgather_enabled() and _try_all_gather(cache, key, user_state_dict):
+        return
     if key not in cache.handles:
         num_ranks = await store.get(f"{key}/num_ranks")
         all_handles = defaultdict(list)
