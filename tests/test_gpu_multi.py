@@ -68,6 +68,19 @@ def _free_port():
     return p
 
 
+def _free_ports(n):
+    """n distinct free ports (all sockets held open until every port is chosen)."""
+    socks = []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        socks.append(s)
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
 def _ipc_worker(rank, world, port, pg_port, outdir, same_gpu):
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(0 if same_gpu else rank), "WORLD_SIZE": str(world),
                        "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
@@ -134,7 +147,7 @@ def test_two_process_ipc_direct_sync_and_store(same_gpu):
     if not same_gpu and _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     world = 2
-    port, pg_port = _free_port(), _free_port()
+    port, pg_port = _free_ports(2)
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_ipc_worker, args=(world, port, pg_port, d, same_gpu), nprocs=world, join=True)
         for r in range(world):

@@ -22,6 +22,19 @@ def _free_port():
     return port
 
 
+def _free_ports(n):
+    """n distinct free ports (all sockets held open until every port is chosen)."""
+    socks = []
+    for _ in range(n):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        socks.append(s)
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
 def _worker(rank, world, port, pg_port, outdir):
     os.environ.update({"RANK": str(rank), "LOCAL_RANK": str(rank), "WORLD_SIZE": str(world),
                        "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
@@ -68,7 +81,7 @@ def _worker(rank, world, port, pg_port, outdir):
 
 def test_two_rank_spmd_store_on_cpu():
     world = 2
-    port, pg_port = _free_port(), _free_port()
+    port, pg_port = _free_ports(2)
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, port, pg_port, d), nprocs=world, join=True)
         out = [json.load(open(os.path.join(d, f"{r}.json"))) for r in range(world)]
