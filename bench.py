@@ -150,7 +150,7 @@ def emit(obj):
 # =================================================================================================
 # reference arm / cpu baseline: the oracle's port of the reference's shm path on the host
 # =================================================================================================
-def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 20.0):
+def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 20.0, layers: int | None = None):
     """Time put_state_dict + get_state_dict of the reference's SharedMemory path, restated:
     put = every source shard copied into its shm segment (transport/shared_memory.py:373-374);
     get = every stored rectangle that intersects the wanted slice copied segment -> destination
@@ -165,7 +165,8 @@ def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 2
     from torchstore_b200 import _native  # struct definition only (no GPU call)
 
     cores = os.cpu_count() or 1
-    layers = 4 if n_ranks > 1 else 2
+    if layers is None:
+        layers = 4 if n_ranks > 1 else 2
     layout = workloads.llama_layout(workloads.LLAMA3_8B, n_layers=layers, with_embeddings=False)
     sample_bytes = workloads.state_dict_bytes(layout)
     rng = np.random.default_rng(0)
