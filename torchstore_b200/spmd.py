@@ -163,7 +163,7 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
     # k-th initialisation of this store name in this job: every rank bumps its own counter, so all
     # ranks derive the same generation and never read keys of an earlier incarnation
     gen = int(rendezvous.add(_spmd_key(store_name, f"generation/{env.rank}"), 1))
-    server = rpc.ActorServer.instance()
+    rpc.ActorServer.instance()  # start this process' actor server (idempotent)
     owned: list[str] = []
     hosts_volume = isinstance(strategy, LocalRankStrategy) or env.local_rank == 0
     if hosts_volume:
@@ -193,7 +193,6 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
         rendezvous.set(controller_key, pickle.dumps(controller))
     else:
         controller = pickle.loads(rendezvous.get(controller_key))
-    del server
     _api._spmd_state_map[store_name] = _SPMDSession(rendezvous=rendezvous, controller=controller, store_name=store_name,
                                                    is_primary=(env.rank == 0), env=env, owned_actors=owned, generation=gen)
 

@@ -191,14 +191,6 @@ async def _wait(device: int) -> None:
     done.close()
 
 
-def _client_device(tensor: torch.Tensor | None, fallback: int | None) -> int:
-    if tensor is not None and tensor.is_cuda:
-        return tensor.device.index
-    if fallback is not None:
-        return fallback
-    return torch.cuda.current_device()
-
-
 class HbmTransportBuffer(TransportBuffer):
     supports_inplace_resharding = True
     supports_batch_puts = True
