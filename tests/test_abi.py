@@ -46,3 +46,28 @@ def test_no_gpu_means_loud_failure_not_fallback():
         _native.init()
     with pytest.raises(_native.TsbError):
         _native.plan_create(0, _native.make_rect_array(1), 0)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback when the CUDA extension is absent: first use raises with build instructions."""
+    import pytest
+
+    monkeypatch.setenv("TSTORE_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_native, "_lib", None)
+    with pytest.raises(RuntimeError, match="libtstore_b200.so not found"):
+        _native.lib()
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _native.init()
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under torchstore_b200/ may import it."""
+    pkg = os.path.join(REPO_ROOT, "torchstore_b200")
+    offenders = []
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(root, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M):
+                    offenders.append(os.path.join(root, f))
+    assert offenders == []
