@@ -149,3 +149,26 @@ def test_unequal_sources_are_spread_proportionally():
     gaps = np.diff(pos)
     assert gaps.min() >= 5 and gaps.max() <= 7  # one remote tile every ~6 tiles, start to finish
     assert pos[0] <= 6 and pos[-1] >= len(order) - 7
+
+
+def test_oracle_threaded_copy_equals_single_threaded():
+    """bench.py's cpu_baseline uses the oracle's pthread driver; it must move exactly the same bytes
+    as the single-threaded path (row-balanced partition across rect boundaries)."""
+    rng = random.Random(77)
+    cases = [random_case(rng, cast=(i % 3 == 0), max_elems=1 << 18) for i in range(40)]
+    # a few big contiguous ones so that total bytes >> 1 MiB and partitions cut inside rects
+    a = materialise(cases, "cpu", 3)
+    big_src = torch.arange(1 << 21, dtype=torch.int32)
+    big_a = torch.zeros_like(big_src)
+    a.append((big_src.reshape(2048, 1024)[:, 100:900], big_a.reshape(2048, 1024)[:, 100:900], big_a, big_src))
+    ra, na = rects_for(a)
+    c_oracle.copy_rects(ra, na, nan_mode=0, nthreads=1)
+    for threads in (2, 7, 16):
+        # re-materialise the destinations so untouched bytes match too
+        b2 = materialise(cases, "cpu", 3)
+        big_c = torch.zeros_like(big_src)
+        b2.append((big_src.reshape(2048, 1024)[:, 100:900], big_c.reshape(2048, 1024)[:, 100:900], big_c, big_src))
+        r2, n2 = rects_for(b2)
+        c_oracle.copy_rects(r2, n2, nan_mode=0, nthreads=threads)
+        for (_, _, da, _), (_, _, d2, _) in zip(a, b2):
+            assert np.array_equal(bytes_of(da), bytes_of(d2)), threads
