@@ -224,6 +224,13 @@ def cpu_reference_run(n_ranks: int, steps: int, warmup: int, budget_s: float = 2
 
     for _ in range(max(1, warmup)):
         one_sync()
+    # the baseline must be doing the real work: every destination rectangle equals its source slice
+    for drank in range(n_ranks):
+        for name, srank, s_idx, d_idx, _exact in workloads.fsdp_to_tp_rects(layout, n_ranks, drank):
+            got = dst[(name, drank)][tuple(slice(a, b) for a, b in d_idx)]
+            want = src[(name, srank)][tuple(slice(a, b) for a, b in s_idx)]
+            if not np.array_equal(got, want):
+                raise SystemExit(f"cpu reference port produced wrong bytes for {name} ({srank}->{drank})")
     t0 = time.perf_counter()
     done = 0
     while done < steps and (time.perf_counter() - t0 < budget_s or done == 0):
