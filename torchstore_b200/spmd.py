@@ -109,9 +109,20 @@ class _SPMDSession:
                 except Exception as e:  # noqa: BLE001
                     err, status = e, repr(e)
                 self.rendezvous.set(_spmd_key(name, "shutdown", gen), status)
+                # the primary may own the rendezvous server: keep it alive until every other rank
+                # has read the outcome (otherwise their pending get dies with "connection reset")
+                import time
+
+                deadline = time.time() + 30
+                while self.rendezvous.add(_spmd_key(name, "shutdown_acks", gen), 0) < self.env.world_size - 1:
+                    if time.time() > deadline:
+                        logger.warning("TorchStore shutdown: not every rank acknowledged within 30 s")
+                        break
+                    time.sleep(0.002)
             else:
                 try:
                     status = self.rendezvous.get(_spmd_key(name, "shutdown", gen)).decode()
+                    self.rendezvous.add(_spmd_key(name, "shutdown_acks", gen), 1)
                 except Exception as e:
                     raise RuntimeError("Timed out waiting for TorchStore shutdown") from e
                 if status != "ok":
@@ -136,11 +147,22 @@ def _validate_strategy(strategy) -> HostStrategy | LocalRankStrategy:
     raise RuntimeError("SPMD mode requires an explicit HostStrategy or LocalRankStrategy")
 
 
+_rendezvous_cache: dict[tuple, Any] = {}
+
+
 def _open_rendezvous(env: SPMDEnv, timeout: timedelta):
-    # under torchrun the elastic agent already serves a TCPStore on MASTER_PORT: join it as a client
-    agent_store = os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "False") == "True"
-    return TCPStore(env.master_addr, env.master_port, env.world_size,
-                    is_master=(env.rank == 0 and not agent_store), timeout=timeout, wait_for_workers=False)
+    """TCPStore on MASTER_ADDR:MASTER_PORT, created once per process and kept for its lifetime: a
+    store that is shut down and re-initialised in the same job must not race a dying server against
+    a new one on the same port."""
+    key = (env.master_addr, env.master_port, env.rank, env.world_size)
+    store = _rendezvous_cache.get(key)
+    if store is None:
+        # under torchrun the elastic agent already serves a TCPStore on MASTER_PORT: join it as a client
+        agent_store = os.environ.get("TORCHELASTIC_USE_AGENT_STORE", "False") == "True"
+        store = TCPStore(env.master_addr, env.master_port, env.world_size,
+                         is_master=(env.rank == 0 and not agent_store), timeout=timeout, wait_for_workers=False)
+        _rendezvous_cache[key] = store
+    return store
 
 
 async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str = _api.DEFAULT_TORCHSTORE_NAME, *,
