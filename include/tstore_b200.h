@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TSB_ABI_VERSION 1
+#define TSB_ABI_VERSION 2
 #define TSB_MAX_DIMS 6
 
 enum {
@@ -137,14 +137,18 @@ enum {
 
 typedef struct tsb_plan_info {
   uint64_t num_rects;
-  uint64_t num_tiles;
+  uint64_t num_tiles;         /* copy queue: tiles moved by the copy warps (LDG.128/STG.128) */
   uint64_t payload_bytes;     /* sum over rects of bytes written to dst */
   uint64_t src_bytes;         /* sum over rects of bytes read from src */
-  uint64_t remote_src_bytes;  /* part of src_bytes with src_device != plan device */
+  uint64_t remote_src_bytes;  /* part of src_bytes with src_device != plan device (NVLink bytes) */
+  uint64_t num_link_tiles;    /* link queue: tiles moved by the link warp's TMA bulk ring */
+  uint64_t link_bytes;        /* part of remote_src_bytes that travels through the link queue */
   uint32_t grid;              /* CTAs per launch */
-  uint32_t block;             /* threads per CTA */
-  uint32_t tile_bytes;
+  uint32_t block;             /* threads per CTA: 256 copy threads (+32 link threads) */
+  uint32_t tile_bytes;        /* copy-queue tile size */
   uint32_t num_vector_rects;  /* rects moved with 16-byte accesses */
+  uint32_t link_tile_bytes;   /* link-queue tile size == one ring stage */
+  uint32_t link_stages;       /* ring depth */
 } tsb_plan_info_t;
 
 /* Is (src_dtype -> dst_dtype) implemented?  Same dtype is always supported. */
@@ -156,6 +160,17 @@ int tsb_plan_create(int device, const tsb_rect_t* rects, uint64_t n, uint32_t fl
 int tsb_plan_info(tsb_plan_t plan, tsb_plan_info_t* out);
 /* One persistent-kernel launch that moves every rect of the plan.  Asynchronous. */
 int tsb_plan_run(tsb_plan_t plan, void* stream);
+/* The whole per-sync sequence of DirectWeightSyncDest.pull (direct_weight_sync.py:319-350) in one
+ * call, on the device's copy stream: [copy stream waits for everything queued on caller_stream]
+ * -> start event -> kernel -> done event -> [caller_stream waits for the done event].  The events
+ * belong to the plan and are reused.  caller_stream == NULL skips both fences. */
+int tsb_plan_launch(tsb_plan_t plan, void* caller_stream);
+/* Completion of the last tsb_plan_launch: 1 = bytes are in destination HBM, 0 = still running
+ * (the await point of `await asyncio.gather(*reads)`, direct_weight_sync.py:338-340). */
+int tsb_plan_poll(tsb_plan_t plan, int* out_done);
+int tsb_plan_wait(tsb_plan_t plan);
+/* Device time of the last tsb_plan_launch (start event -> done event). */
+int tsb_plan_elapsed_ms(tsb_plan_t plan, float* out_ms);
 int tsb_plan_destroy(tsb_plan_t plan);
 /* Host-only (no CUDA call): compile and copy the kernel tables out, for inspection and for the
  * CPU test-suite, which replays them against the oracle.  out_rects: records of 192 bytes,
@@ -163,8 +178,11 @@ int tsb_plan_destroy(tsb_plan_t plan);
 int tsb_plan_compile_host(int device, const tsb_rect_t* rects, uint64_t n, uint32_t flags, uint32_t tile_units,
                           void* out_rects, uint64_t n_rect_cap, uint64_t* out_n_rects, void* out_tiles,
                           uint64_t n_tile_cap, uint64_t* out_n_tiles, tsb_plan_info_t* out_info);
-/* Convenience: create + run + destroy-when-done (uncached store-path gets). */
+/* One-shot (uncached store-path puts/gets): compile, upload the tables and launch on ONE stream;
+ * table buffers come from a recycled pinned/device pool, so a warm call does no cudaMalloc/cudaFree. */
 int tsb_copy_rects(int device, const tsb_rect_t* rects, uint64_t n, uint32_t flags, void* stream);
+/* Table-pool counters (tests / diagnostics). */
+int tsb_pool_stats(uint64_t* out_blocks, uint64_t* out_allocs, uint64_t* out_reuses);
 
 /* ------------------------------------------------------------------------------------------ */
 /* streams and events (the await points of the reference's coroutines)                         */

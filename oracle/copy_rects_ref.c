@@ -264,7 +264,9 @@ typedef struct {
   int64_t dst_stride[6];
   uint32_t ext[6];
   uint32_t n_outer, rows, units_per_row, magic, wide, split, mode, src_unit_bytes, dst_unit_bytes;
-  uint32_t pad_[5];
+  uint32_t tile_units; /* tile size of this rect (link-queue rects use the TMA stage size) */
+  uint32_t link;       /* 1: the rect's tiles are in the link queue (moved by TMA bulk copies) */
+  uint32_t pad_[3];
 } dev_rect_t;
 
 static void mode_dtypes(uint32_t mode, uint32_t* sdt, uint32_t* ddt, uint32_t* elems) {
@@ -315,6 +317,14 @@ int oracle_replay_plan(const void* rect_table, uint64_t n_rects, const uint32_t*
     if (sdt == 0xff) return -3;
     const uint32_t es = dtype_size(sdt), ed = dtype_size(ddt);
     if (es * elems != r->src_unit_bytes || ed * elems != r->dst_unit_bytes) return -4;
+    if (r->tile_units) tile_units = r->tile_units; /* per-rect tile size wins over the caller's default */
+    if (r->link) {
+      /* what the link warp's bulk copies can express: 16-byte units, rows addressed by one stride,
+       * a tile never larger than one ring stage */
+      if (r->mode != 4 || (!r->wide && r->n_outer > 1)) return -10;
+      uint64_t tile_bytes = r->wide ? (uint64_t)tile_units * 16 : (uint64_t)r->split * r->units_per_row * 16;
+      if (tile_bytes > (uint64_t)tile_units * 16) return -11;
+    }
     if (r->wide) {
       uint32_t row = tir / r->split, seg = tir - row * r->split;
       if (row >= r->rows) return -5;

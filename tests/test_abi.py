@@ -33,7 +33,7 @@ def test_abi_version_and_struct_sizes():
     assert _native.lib().tsb_abi_version() == _native.TSB_ABI_VERSION
     assert C.sizeof(_native.Region) == 64 + 8 * 4 + 4 * 2 + 8
     assert C.sizeof(_native.Rect) == 16 + 3 * 6 * 8 + 16
-    assert C.sizeof(_native.PlanInfo) == 5 * 8 + 4 * 4
+    assert C.sizeof(_native.PlanInfo) == 7 * 8 + 6 * 4
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

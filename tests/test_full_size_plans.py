@@ -58,7 +58,8 @@ def fake_windows(layout, n, dest_rank):
 
 DEV_RECT = np.dtype([("src", "<u8"), ("dst", "<u8"), ("ss", "<i8", 6), ("ds", "<i8", 6), ("ext", "<u4", 6),
                      ("n_outer", "<u4"), ("rows", "<u4"), ("upr", "<u4"), ("magic", "<u4"), ("wide", "<u4"),
-                     ("split", "<u4"), ("mode", "<u4"), ("sub", "<u4"), ("dub", "<u4"), ("pad", "<u4", 5)])
+                     ("split", "<u4"), ("mode", "<u4"), ("sub", "<u4"), ("dub", "<u4"), ("tile_units", "<u4"),
+                     ("link", "<u4"), ("pad", "<u4", 3)])
 assert DEV_RECT.itemsize == 192
 
 
@@ -80,7 +81,22 @@ def test_llama3_8b_plans_match_reference_statistics_and_cover_exactly(n):
         local = sum(int(np.prod(s.shape)) * 2 for s, _ in pairs if s.device == dest_rank)
         assert info.remote_src_bytes == info.src_bytes - local
         dr = table.view(DEV_RECT)
-        tile_units = info.tile_bytes // 16
+        # two queues: remote 16-byte rects ride the link queue (TMA bulk ring, small tiles), the rest
+        # the copy queue; the tile list is copy queue first, then link queue
+        is_link = dr["link"] == 1
+        src_dev = np.array([p[0].device for p in pairs])
+        assert len(dr) == len(pairs)  # rects map 1:1 to pairs here (no splitting at these sizes)
+        assert np.array_equal(is_link, src_dev != dest_rank)
+        assert info.link_bytes == info.remote_src_bytes
+        tile_units = np.where(is_link, info.link_tile_bytes // 16, info.tile_bytes // 16)
+        assert np.array_equal(dr["tile_units"], tile_units)
+        assert len(tiles) == info.num_tiles + info.num_link_tiles
+        assert not is_link[tiles[: info.num_tiles, 0]].any() and is_link[tiles[info.num_tiles:, 0]].all()
+        # a link tile is never larger than one ring stage
+        stage_units = info.link_tile_bytes // 16
+        lk = dr[is_link]
+        assert np.all(np.where(lk["wide"] == 1, stage_units, lk["split"].astype(np.int64) * lk["upr"]) <= stage_units)
+        assert np.all((lk["wide"] == 1) | (lk["n_outer"] <= 1))
         # per-rect tile counts, every (rect, tile) exactly once
         per_rect = np.bincount(tiles[:, 0], minlength=len(dr))
         wide = dr["wide"] == 1
@@ -90,8 +106,8 @@ def test_llama3_8b_plans_match_reference_statistics_and_cover_exactly(n):
         assert len(np.unique(key)) == len(key)
         # units covered == units of the rect (wide: segments of tile_units; narrow: whole rows)
         assert int((dr["rows"].astype(np.int64) * dr["upr"] * dr["dub"]).sum()) == info.payload_bytes
-        assert np.all(dr["split"][wide] == -(-dr["upr"][wide].astype(np.int64) // tile_units))
-        assert np.all(dr["upr"][~wide] < tile_units)
+        assert np.all(dr["split"][wide] == -(-dr["upr"][wide].astype(np.int64) // tile_units[wide]))
+        assert np.all(dr["upr"][~wide] < tile_units[~wide])
         # multiply-high division exact over the index range a narrow tile can see
         for r in dr[~wide][:50]:
             u = int(r["upr"])
@@ -102,14 +118,13 @@ def test_llama3_8b_plans_match_reference_statistics_and_cover_exactly(n):
         # source interleave: within any window of 4*n consecutive tiles (while all sources still have
         # work) every source GPU appears
         if n > 1:
-            src_dev_of_rect = np.array([p[0].device for p in pairs])
-            # rects map 1:1 to pairs here (no splitting at these sizes)
-            assert len(dr) == len(pairs)
-            devs = src_dev_of_rect[tiles[:, 0]]
-            remote = devs[devs != dest_rank]
-            head = remote[: len(remote) // 2]
-            for start in range(0, max(1, len(head) - 4 * n), max(1, len(head) // 64)):
-                assert len(set(head[start:start + 4 * n].tolist())) == n - 1
+            # link queue: granules of 8 tiles (one claim) rotate over the n-1 source GPUs
+            devs = src_dev[tiles[info.num_tiles:, 0]]
+            assert (devs != dest_rank).all()
+            head = devs[: len(devs) // 2]
+            win = 8 * 4 * n
+            for start in range(0, max(1, len(head) - win), max(1, len(head) // 64)):
+                assert len(set(head[start:start + win].tolist())) == n - 1
 
 
 def test_config2_single_4gib_rect_compiles_to_one_wide_row():
@@ -118,8 +133,9 @@ def test_config2_single_4gib_rect_compiles_to_one_wide_row():
     rects, k = build_rects([(src, dst)])
     table, tiles, info = _native.plan_compile_host(1, rects, k, 0, 0)
     assert info.payload_bytes == 4 << 30 and info.remote_src_bytes == 4 << 30
-    assert info.num_rects == 1 and info.num_tiles == (4 << 30) // info.tile_bytes
+    assert info.num_rects == 1 and info.num_tiles == 0 and info.num_link_tiles == (4 << 30) // info.link_tile_bytes
     dr = table.view(DEV_RECT)[0]
+    assert dr["link"] == 1
     assert dr["wide"] == 1 and dr["rows"] == 1 and dr["upr"] == (4 << 30) // 16 and dr["mode"] == 4
 
 

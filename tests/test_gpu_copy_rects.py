@@ -30,7 +30,7 @@ def run_product(pairs, device=0, flags=0):
     before = _native.launch_count()
     _native.plan_run(plan, None)
     _native.stream_sync(device, None)
-    assert _native.launch_count() == before + (1 if info.num_tiles else 0)
+    assert _native.launch_count() == before + (1 if info.num_tiles or info.num_link_tiles else 0)
     _native.plan_destroy(plan)
     return info
 
@@ -38,11 +38,18 @@ def run_product(pairs, device=0, flags=0):
 @pytest.mark.parametrize("seed", [0, 1, 2])
 @pytest.mark.parametrize("cast", [False, True])
 @pytest.mark.parametrize("force_generic", [False, True])
-def test_random_rects_match_oracle(seed, cast, force_generic, monkeypatch):
+@pytest.mark.parametrize("link", ["default", "all"])
+def test_random_rects_match_oracle(seed, cast, force_generic, link, monkeypatch):
+    """link="all" (TSB_LINK=2) routes every 16-byte-unit rect through the link warp's TMA bulk ring
+    even though the sources are local, so the NVLink data path is parity-tested on one GPU."""
     if force_generic:
         monkeypatch.setenv("TSB_FORCE_GENERIC", "1")
     else:
         monkeypatch.delenv("TSB_FORCE_GENERIC", raising=False)
+    if link == "all":
+        monkeypatch.setenv("TSB_LINK", "2")
+    else:
+        monkeypatch.delenv("TSB_LINK", raising=False)
     rng = random.Random(1000 * seed + cast)
     cases = [random_case(rng, cast=cast, max_elems=1 << 18) for _ in range(80)]
     host = materialise(cases, "cpu", seed)
@@ -91,7 +98,17 @@ def test_large_contiguous_int32_is_bit_exact():
     assert int(dst.view(torch.int64).sum().item()) == int(src.view(torch.int64).sum().item())
 
 
-def test_narrow_row_reshard_shapes():
+@pytest.fixture(params=["default", "all"])
+def link_mode(request, monkeypatch):
+    """"all" = TSB_LINK=2: the link warp (TMA bulk ring) moves every 16-byte-unit rect."""
+    if request.param == "all":
+        monkeypatch.setenv("TSB_LINK", "2")
+    else:
+        monkeypatch.delenv("TSB_LINK", raising=False)
+    return request.param
+
+
+def test_narrow_row_reshard_shapes(link_mode):
     """wo / w2 style rectangles: 512 x 512 and 512 x 1792 bf16 windows with 8 KiB / 28 KiB source
     pitch, written into a [4096, 512] / [4096, 1792] destination."""
     for cols_total, cols in ((4096, 512), (14336, 1792)):
@@ -101,11 +118,78 @@ def test_narrow_row_reshard_shapes():
             pairs = [(srcs[s][:, r * cols:(r + 1) * cols], dst[s * 512:(s + 1) * 512]) for s in range(8)]
             info = run_product(pairs)
             assert info.num_vector_rects == 8
+            assert (info.num_link_tiles > 0 and info.num_tiles == 0) if link_mode == "all" else info.num_link_tiles == 0
             want = torch.cat([s[:, r * cols:(r + 1) * cols] for s in srcs], dim=0)
             assert torch.equal(dst, want)
 
 
-def test_many_tiny_and_one_huge_in_one_launch():
+@pytest.mark.parametrize("stage_bytes,stages", [(8192, 6), (4096, 3), (16384, 4), (1024, 8)])
+def test_link_ring_geometries(stage_bytes, stages, monkeypatch):
+    """Every ring geometry the plan compiler accepts moves the same bytes: wide rows cut into stage-sized
+    segments, narrow rows packed several per stage, strided destinations (per-row stores) and
+    contiguous ones (one store per stage), 3-D wide rects, and a copy-queue rect beside them."""
+    monkeypatch.setenv("TSB_LINK", "2")
+    monkeypatch.setenv("TSB_LINK_STAGE_BYTES", str(stage_bytes))
+    monkeypatch.setenv("TSB_LINK_STAGES", str(stages))
+    g = torch.Generator(device="cuda").manual_seed(stage_bytes + stages)
+
+    def rnd(*shape):
+        return torch.randint(-30000, 30000, shape, dtype=torch.int16, device="cuda", generator=g)
+
+    a = rnd(300, 1000)       # rows of 2000 B -> 8-byte units: stays in the copy queue
+    b = rnd(1 << 21)         # one wide row (4 MiB)
+    c = rnd(777, 4096)       # narrow 1 KiB windows, source pitch 8 KiB, destination contiguous
+    d = rnd(64, 3, 20000)    # wide rows (16 KiB windows of 40 KB rows) under two outer dims
+    e = rnd(512, 1792 * 8)   # 3.5 KiB windows into a strided destination
+    e_dst = torch.zeros(512, 4096, dtype=torch.int16, device="cuda")
+    outs = [torch.zeros_like(a), torch.zeros_like(b), torch.zeros(777, 512, dtype=torch.int16, device="cuda"),
+            torch.zeros(64, 3, 8192, dtype=torch.int16, device="cuda")]
+    pairs = [(a, outs[0]), (b, outs[1]), (c[:, 1024:1536], outs[2]), (d[:, :, 4096:12288], outs[3]),
+             (e[:, 1792:3584], e_dst[:, 1024:2816])]
+    info = run_product(pairs)
+    assert info.link_tile_bytes == stage_bytes and info.link_stages == stages
+    assert info.num_link_tiles > 0 and info.num_tiles > 0
+    assert torch.equal(outs[0], a) and torch.equal(outs[1], b)
+    assert torch.equal(outs[2], c[:, 1024:1536]) and torch.equal(outs[3], d[:, :, 4096:12288])
+    assert torch.equal(e_dst[:, 1024:2816], e[:, 1792:3584])
+    assert int(e_dst[:, :1024].abs().sum()) == 0 and int(e_dst[:, 2816:].abs().sum()) == 0
+
+
+def test_fenced_launch_poll_and_elapsed():
+    """tsb_plan_launch: fence-in on the caller's stream, kernel, fence-out -- torch work queued before
+    is seen by the copy and torch work queued after sees the copy, with no host wait in between."""
+    a = torch.zeros(1 << 24, dtype=torch.int32, device="cuda")
+    b = torch.zeros_like(a)
+    rects, n = build_rects([(StridedMem.from_tensor(a), StridedMem.from_tensor(b))])
+    plan = _native.plan_create(0, rects, n)
+    assert _native.plan_poll(plan)  # never launched: trivially done
+    for i in range(1, 4):
+        a.fill_(i)  # queued on torch's stream, not waited for
+        _native.plan_launch(plan, _native.torch_stream(0))
+        c = b + 0   # torch stream waits for the done event
+        _native.plan_wait(plan)
+        assert _native.plan_poll(plan)
+        assert _native.plan_elapsed_ms(plan) > 0
+        assert int(c.min()) == i and int(c.max()) == i
+    _native.plan_destroy(plan)
+
+
+def test_one_shot_tables_come_from_a_recycled_pool():
+    a = torch.arange(1 << 16, dtype=torch.int64, device="cuda")
+    outs = [torch.zeros_like(a) for _ in range(40)]
+    before = _native.pool_stats()
+    for o in outs:
+        rects, n = build_rects([(StridedMem.from_tensor(a), StridedMem.from_tensor(o))])
+        _native.copy_rects(0, rects, n)
+    _native.stream_sync(0, None)
+    after = _native.pool_stats()
+    assert all(torch.equal(a, o) for o in outs)
+    # back-to-back calls may need a few blocks in flight at once, never one per call
+    assert after["allocs"] - before["allocs"] <= 16
+    assert after["reuses"] - before["reuses"] >= 24
+
+
+def test_many_tiny_and_one_huge_in_one_launch(link_mode):
     tiny_src = [torch.randn(512, device="cuda").to(torch.bfloat16) for _ in range(300)]
     tiny_dst = [torch.zeros(512, dtype=torch.bfloat16, device="cuda") for _ in range(300)]
     big_src = torch.randn(64 << 20, device="cuda").to(torch.bfloat16)

@@ -21,7 +21,7 @@ def _run(cases, seed, tile_units, flags=0):
     assert n_a == n_b
     c_oracle.copy_rects(rects_a, n_a, nan_mode=0)
     table, tiles, info = _native.plan_compile_host(0, rects_b, n_b, flags, tile_units)
-    assert info.num_tiles == tiles.shape[0]
+    assert info.num_tiles + info.num_link_tiles == tiles.shape[0]
     c_oracle.replay_plan(table, tiles, info.tile_bytes // 16, nan_mode=0)
     for (sa, da, dbase_a, _), (sb, db, dbase_b, _) in zip(a, b):
         assert np.array_equal(bytes_of(dbase_a), bytes_of(dbase_b))
@@ -30,7 +30,11 @@ def _run(cases, seed, tile_units, flags=0):
 
 @pytest.mark.parametrize("tile_units", [64, 256, 4096])
 @pytest.mark.parametrize("cast", [False, True])
-def test_compiled_plan_replays_to_oracle_result(tile_units, cast):
+@pytest.mark.parametrize("link", ["1", "2"])
+def test_compiled_plan_replays_to_oracle_result(tile_units, cast, link, monkeypatch):
+    # TSB_LINK=2 routes every eligible 16-byte-unit rect through the link queue (small tiles, one
+    # ring stage each); the interpreter also checks what a link tile may look like
+    monkeypatch.setenv("TSB_LINK", link)
     rng = random.Random(100 + tile_units + cast)
     cases = [random_case(rng, cast=cast) for _ in range(60)]
     _run(cases, seed=5, tile_units=tile_units)
@@ -47,8 +51,10 @@ def test_same_dtype_result_equals_torch_copy():
         assert np.array_equal(bytes_of(dbase), bytes_of(rbase))
 
 
-def test_tile_order_interleaves_sources_and_covers_everything():
+def test_tile_order_interleaves_sources_and_covers_everything(monkeypatch):
     # 3 "sources" (devices 1,2,3) feeding device 0, equal sizes: tiles must rotate 1,2,3,1,2,3...
+    # (copy queue: TSB_LINK=0 keeps NVLink sources with the copy warps)
+    monkeypatch.setenv("TSB_LINK", "0")
     src = [torch.arange(64 * 1024, dtype=torch.int32) + i for i in range(3)]
     dst = torch.zeros(3, 64 * 1024, dtype=torch.int32)
     from torchstore_b200.planner import StridedMem, build_rects
@@ -73,6 +79,17 @@ def test_tile_order_interleaves_sources_and_covers_everything():
     # NO_INTERLEAVE keeps rect order
     _, tiles2, _ = _native.plan_compile_host(0, rects, n, _native.TSB_PLAN_NO_INTERLEAVE, 256)
     assert tiles2[:, 0].tolist() == sorted(tiles2[:, 0].tolist())
+    # default: NVLink sources ride the link queue -- 8 KiB tiles, rotated in granules of 8 (one claim)
+    monkeypatch.delenv("TSB_LINK")
+    dst.zero_()
+    table, tiles, info = _native.plan_compile_host(0, rects, n, 0, 256)
+    assert info.num_tiles == 0 and info.num_link_tiles == 3 * 32 and info.link_bytes == info.remote_src_bytes
+    assert info.block == 256 + 32
+    assert tiles[:, 0].tolist()[:32] == [0] * 8 + [1] * 8 + [2] * 8 + [0] * 8
+    assert len(set(map(tuple, tiles.tolist()))) == 3 * 32
+    c_oracle.replay_plan(table, tiles, 256)
+    for i in range(3):
+        assert torch.equal(dst[i], src[i])
 
 
 def test_vector_mode_selection_and_alignment_fallbacks():
@@ -130,9 +147,12 @@ def test_unsupported_cast_is_rejected():
         build_rects([(StridedMem.from_tensor(a), StridedMem.from_tensor(b))])
 
 
-def test_unequal_sources_are_spread_proportionally():
-    """A small remote share must be spread over the whole launch, not bunched at the front."""
+def test_unequal_sources_are_spread_proportionally(monkeypatch):
+    """A small remote share in the COPY queue (link queue off) must be spread over the whole launch,
+    not bunched at the front."""
     from torchstore_b200.planner import StridedMem, build_rects
+
+    monkeypatch.setenv("TSB_LINK", "0")
 
     big = torch.zeros(5 * 64 * 1024, dtype=torch.int32)   # local: 5x the tiles
     small = torch.zeros(64 * 1024, dtype=torch.int32)     # remote

@@ -64,13 +64,20 @@ def main():
             e1.record()
             e1.synchronize()
         rec(name="torch_copy_peer_4GiB", ms=round(e0.elapsed_time(e1), 4), GBps=round(n / e0.elapsed_time(e1) / 1e6, 1))
-    for per_sm in (1, 2, 3, 4, 6, 8):
-        for tile in (32768, 65536, 131072):
+    # link=0: copy warps pull with LDG.128; link=1: link warp's TMA bulk ring (default)
+    for link, stage, stages in ((0, 8192, 6), (1, 8192, 6), (1, 16384, 4), (1, 4096, 8)):
+        for per_sm in (2, 3, 4):
+            os.environ["TSB_LINK"] = str(link)
+            os.environ["TSB_LINK_STAGE_BYTES"] = str(stage)
+            os.environ["TSB_LINK_STAGES"] = str(stages)
             os.environ["TSB_CTAS_PER_SM"] = str(per_sm)
-            os.environ["TSB_TILE_BYTES"] = str(tile)
             dst.zero_()
             ms, info = time_plan(1, [(src, dst)])
-            rec(name="pull_contig_4GiB", ctas_per_sm=per_sm, tile_bytes=tile, ms=round(ms, 4), GBps=round(n / ms / 1e6, 1))
+            rec(name="pull_contig_4GiB", link=link, stage_bytes=stage, stages=stages, ctas_per_sm=per_sm, ms=round(ms, 4),
+                GBps=round(n / ms / 1e6, 1), grid=info["grid"], block=info["block"])
+    os.environ["TSB_LINK_STAGE_BYTES"] = "8192"
+    os.environ["TSB_LINK_STAGES"] = "6"
+    os.environ["TSB_LINK"] = "1"
     assert torch.equal(src.cpu()[:1 << 20], dst.cpu()[:1 << 20]) and int(dst.view(torch.int16).to(torch.int64).sum()) == int(src.view(torch.int16).to(torch.int64).sum())
     # push (GPU0 writes into GPU1 memory): store-path puts to a remote volume
     os.environ["TSB_CTAS_PER_SM"] = "3"
@@ -85,10 +92,15 @@ def main():
         dstt = torch.zeros(nl, 4096, cols, dtype=torch.bfloat16, device="cuda:1")
         pairs = [(srcs[layer, s][:, 3 * cols:4 * cols], dstt[layer][s * 512:(s + 1) * 512]) for layer in range(nl) for s in range(8)]
         payload = dstt.numel() * 2
-        for per_sm in (2, 3, 4, 8):
-            os.environ["TSB_CTAS_PER_SM"] = str(per_sm)
-            ms, info = time_plan(1, pairs)
-            rec(name=f"pull_{label}", ctas_per_sm=per_sm, ms=round(ms, 4), GBps=round(payload / ms / 1e6, 1), rects=info["num_rects"])
+        for link in (0, 1):
+            for per_sm in (2, 3, 4):
+                os.environ["TSB_LINK"] = str(link)
+                os.environ["TSB_CTAS_PER_SM"] = str(per_sm)
+                dstt.zero_()
+                ms, info = time_plan(1, pairs)
+                rec(name=f"pull_{label}", link=link, ctas_per_sm=per_sm, ms=round(ms, 4), GBps=round(payload / ms / 1e6, 1),
+                    rects=info["num_rects"])
+        os.environ["TSB_LINK"] = "1"
         want = torch.cat([srcs[:, s, :, 3 * cols:4 * cols] for s in range(8)], dim=1)
         assert torch.equal(dstt.cpu(), want.cpu())
         del srcs, dstt, want

@@ -16,7 +16,7 @@ import torch
 from torchstore_b200._build import LIB_PATH
 
 TSB_MAX_DIMS = 6
-TSB_ABI_VERSION = 1
+TSB_ABI_VERSION = 2
 
 TSB_OK, TSB_ERR_INVALID, TSB_ERR_CUDA, TSB_ERR_UNSUPPORTED, TSB_ERR_NOMEM, TSB_ERR_NOTFOUND = range(6)
 
@@ -69,10 +69,14 @@ class PlanInfo(C.Structure):
         ("payload_bytes", C.c_uint64),
         ("src_bytes", C.c_uint64),
         ("remote_src_bytes", C.c_uint64),
+        ("num_link_tiles", C.c_uint64),
+        ("link_bytes", C.c_uint64),
         ("grid", C.c_uint32),
         ("block", C.c_uint32),
         ("tile_bytes", C.c_uint32),
         ("num_vector_rects", C.c_uint32),
+        ("link_tile_bytes", C.c_uint32),
+        ("link_stages", C.c_uint32),
     ]
 
     def as_dict(self) -> dict:
@@ -107,7 +111,12 @@ _SIGNATURES = {
     "tsb_plan_create": (C.c_int, [C.c_int, C.POINTER(Rect), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "tsb_plan_info": (C.c_int, [C.c_uint64, C.POINTER(PlanInfo)]),
     "tsb_plan_run": (C.c_int, [C.c_uint64, _vp]),
+    "tsb_plan_launch": (C.c_int, [C.c_uint64, _vp]),
+    "tsb_plan_poll": (C.c_int, [C.c_uint64, C.POINTER(C.c_int)]),
+    "tsb_plan_wait": (C.c_int, [C.c_uint64]),
+    "tsb_plan_elapsed_ms": (C.c_int, [C.c_uint64, C.POINTER(C.c_float)]),
     "tsb_plan_destroy": (C.c_int, [C.c_uint64]),
+    "tsb_pool_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tsb_plan_compile_host": (
         C.c_int,
         [C.c_int, C.POINTER(Rect), C.c_uint64, C.c_uint32, C.c_uint32, _vp, C.c_uint64, C.POINTER(C.c_uint64),
@@ -280,8 +289,37 @@ def plan_run(plan: int, stream: int | None = None) -> None:
     check(lib().tsb_plan_run(plan, C.c_void_p(stream) if stream else None))
 
 
+def plan_launch(plan: int, caller_stream: int | None = None) -> None:
+    """fence-in, start event, kernel, done event, fence-out: one native call per sync."""
+    check(lib().tsb_plan_launch(plan, C.c_void_p(caller_stream) if caller_stream else None))
+
+
+_poll_flag = C.c_int(0)
+
+
+def plan_poll(plan: int) -> bool:
+    check(lib().tsb_plan_poll(plan, C.byref(_poll_flag)))
+    return bool(_poll_flag.value)
+
+
+def plan_wait(plan: int) -> None:
+    check(lib().tsb_plan_wait(plan))
+
+
+def plan_elapsed_ms(plan: int) -> float:
+    ms = C.c_float(0)
+    check(lib().tsb_plan_elapsed_ms(plan, C.byref(ms)))
+    return float(ms.value)
+
+
 def plan_destroy(plan: int) -> None:
     check(lib().tsb_plan_destroy(plan))
+
+
+def pool_stats() -> dict:
+    b, a, r = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    check(lib().tsb_pool_stats(C.byref(b), C.byref(a), C.byref(r)))
+    return {"blocks": b.value, "allocs": a.value, "reuses": r.value}
 
 
 def copy_rects(device: int, rects, n: int, flags: int = TSB_PLAN_DEFAULT, stream: int | None = None) -> None:

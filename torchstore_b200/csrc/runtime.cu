@@ -39,6 +39,39 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// DeviceGuard
+// ---------------------------------------------------------------------------------------------
+namespace {
+typedef CUresult (*PFN_cuCtxGetCurrent)(CUcontext*);
+PFN_cuCtxGetCurrent ctx_get_current() {
+  static PFN_cuCtxGetCurrent fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return reinterpret_cast<PFN_cuCtxGetCurrent>(p);
+  }();
+  return fn;
+}
+}  // namespace
+
+DeviceGuard::DeviceGuard(int device) {
+  if (PFN_cuCtxGetCurrent get = ctx_get_current()) {
+    CUcontext c = nullptr;
+    had_context = get(&c) == CUDA_SUCCESS && c != nullptr;
+  }
+  err = cudaGetDevice(&prev);
+  if (err != cudaSuccess) { ok = false; return; }
+  // always set: on a thread that never touched CUDA (e.g. the actor-server thread) this is what
+  // binds the primary context, which the driver-API calls below rely on
+  err = cudaSetDevice(device);
+  if (err != cudaSuccess) ok = false;
+  cur = device;
+}
+
+// ---------------------------------------------------------------------------------------------
 // global state
 // ---------------------------------------------------------------------------------------------
 namespace {

@@ -26,18 +26,13 @@ int cuda_fail(cudaError_t e, const char* what);
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
+  bool had_context = true;
   cudaError_t err = cudaSuccess;
-  explicit DeviceGuard(int device) {
-    err = cudaGetDevice(&prev);
-    if (err != cudaSuccess) { ok = false; return; }
-    // always set: on a thread that never touched CUDA (e.g. the actor-server thread) this is what
-    // binds the primary context, which the driver-API calls in runtime.cu rely on
-    err = cudaSetDevice(device);
-    if (err != cudaSuccess) ok = false;
-    cur = device;
-  }
+  explicit DeviceGuard(int device);  // runtime.cu
   ~DeviceGuard() {
-    if (ok && prev >= 0 && prev != cur) cudaSetDevice(prev);
+    // restore only if this thread had a context before: on a fresh thread (the actor-server thread)
+    // "restoring" device 0 would create a primary context on GPU 0 in every rank's process
+    if (ok && had_context && prev >= 0 && prev != cur) cudaSetDevice(prev);
   }
   int cur = -1;
 };
@@ -91,7 +86,9 @@ struct alignas(16) DevRect {
   uint32_t mode;
   uint32_t src_unit_bytes;        // bytes one unit spans in src
   uint32_t dst_unit_bytes;        // bytes one unit spans in dst
-  uint32_t pad_[5];
+  uint32_t tile_units;            // tile size of THIS rect (link rects use the TMA stage size)
+  uint32_t link;                  // 1: tiles of this rect are in the link queue (TMA bulk over NVLink)
+  uint32_t pad_[3];
 };
 static_assert(sizeof(DevRect) == 192, "DevRect layout changed: keep it a multiple of 16 bytes");
 
@@ -103,18 +100,32 @@ struct DevTile {
 // kernel specialisations (see copy_rects.cu)
 enum : uint32_t { KIND_GENERIC = 0, KIND_B16 = 1, KIND_F32_BF16 = 2 };
 
+// Two work queues per plan (see copy_rects.cu):
+//   copy queue  tiles moved by the CTA's 8 copy warps with LDG.128/STG.128 (local HBM sources,
+//               casts, misaligned rects, peer destinations)
+//   link queue  tiles whose source is another GPU's HBM and that move 16-byte units: driven by one
+//               extra "link warp" per CTA through a ring of TMA bulk copies
+//               (peer global -> shared -> local global), fully asynchronous to the copy warps
 struct LaunchParams {
-  const DevTile* tiles;
+  const DevTile* tiles;       // copy queue
   const DevRect* rects;
+  const DevTile* link_tiles;  // link queue (nullptr when empty)
   uint32_t num_tiles;
-  uint32_t tile_units;
+  uint32_t num_link_tiles;
   uint32_t kind;
-  uint32_t* sched;  // {claim counter, finished-CTA counter}; nullptr = fully static striding
+  uint32_t link_stage_bytes;  // bytes per ring stage (== tile size of link rects)
+  uint32_t link_stages;       // ring depth S
+  uint32_t link_lag;          // stores trail loads by this many stages (< S)
+  uint32_t* sched;  // {copy claim, finished CTAs, link claim, pad}; nullptr = fully static striding (no link queue)
 };
 
+constexpr uint32_t kCopyThreads = 256;
+constexpr uint32_t kLinkThreads = 32;
+constexpr uint32_t kLinkBatch = 8;  // link tiles claimed per atomic
+
 // defined in copy_rects.cu
-int launch_copy_rects(const LaunchParams& p, uint32_t grid, uint32_t block, cudaStream_t stream);
+int launch_copy_rects(const LaunchParams& p, uint32_t grid, cudaStream_t stream);
 void count_launch();
-int max_ctas_per_sm(uint32_t kind, int* out);
+int max_ctas_per_sm(uint32_t kind, bool with_link, uint32_t link_smem_bytes, int* out);
 
 }  // namespace tsb

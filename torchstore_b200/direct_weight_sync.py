@@ -29,8 +29,7 @@ from __future__ import annotations
 
 import asyncio
 import logging
-import os
-import time
+import threading
 from collections import defaultdict
 from dataclasses import dataclass
 
@@ -48,20 +47,38 @@ RDMA_KEY_PREFIX = "policy_rdma"
 
 async def wait_event(event: "_native.Event") -> None:
     """Await a CUDA event without blocking the actor's event loop (the reference awaits RDMA
-    completions the same way: everything on the path is a coroutine)."""
+    completions the same way: everything on the path is a coroutine).  Every poll goes through the
+    loop's selector, which drops the GIL, so actor-server threads keep running."""
     spins = 0
     while not event.query():
         spins += 1
-        time.sleep(0)  # hand the GIL to other threads (actor server, samplers) between polls
-        await asyncio.sleep(0 if spins < 2000 else 0.0002)
+        await asyncio.sleep(0 if spins < 4000 else 0.0002)
+
+
+async def wait_plan(plan: int) -> None:
+    """Await the done event of the plan's last fenced launch (tsb_plan_poll)."""
+    spins = 0
+    poll = _native.plan_poll
+    while not poll(plan):
+        spins += 1
+        await asyncio.sleep(0 if spins < 4000 else 0.0002)
+
+
+_fence_events = threading.local()
 
 
 def _fence_in(device: int) -> None:
-    """Copy stream waits for whatever torch has queued on the caller's current stream."""
-    ev = _native.Event(device)
+    """Copy stream waits for whatever torch has queued on the caller's current stream.  One reusable
+    event per (thread, device): cudaStreamWaitEvent snapshots the record it follows, so a later
+    record on the same event does not disturb earlier waits."""
+    cache = getattr(_fence_events, "by_device", None)
+    if cache is None:
+        cache = _fence_events.by_device = {}
+    ev = cache.get(device)
+    if ev is None:
+        ev = cache[device] = _native.Event(device)
     ev.record(_native.torch_stream(device))
     ev.wait_on(device, None)
-    ev.close()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -179,6 +196,7 @@ class DirectWeightSyncSource:
         # name -> (staging_buffer, source_local_tensor)
         self._staging: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}
         self._refresh_plans: dict[int, int] = {}  # device -> native plan id
+        self._devices: tuple[int, ...] = ()  # devices holding registered memory (fence targets)
 
     def register(self, state_dict: dict[str, torch.Tensor], rank: int,
                  transfer_dtype: torch.dtype | None = None,
@@ -207,6 +225,7 @@ class DirectWeightSyncSource:
                 buf = local
             handles[name] = RDMAWeightHandle(rdma_buffer=NvlinkBuffer(buf), tensor_slice=tslice, source_rank=rank)
         self._handles = handles
+        self._devices = tuple(sorted(devices))
         if self._staging:
             self._build_refresh_plans()
             self.refresh()
@@ -230,22 +249,17 @@ class DirectWeightSyncSource:
         """Re-cast the source params into their staging buffers (no-op without transfer_dtype).
         Returns the number of staging buffers refreshed.  Blocks until the cast has landed so the
         caller may publish/notify right after, like the reference's synchronous copy loop."""
-        events = []
         for dev, plan in self._refresh_plans.items():
-            _fence_in(dev)
-            _native.plan_run(plan, None)
-            events.append(_native.Event(dev).record(None))
-        for ev in events:
-            ev.synchronize()
-            ev.close()
+            _native.plan_launch(plan, _native.torch_stream(dev))
+        for plan in self._refresh_plans.values():
+            _native.plan_wait(plan)
         return len(self._staging)
 
     def fence(self) -> None:
         """Make every write queued on the caller's streams (optimizer step, staging refresh) land in
         HBM before readers are told to pull.  The reference has no such fence (its RDMA reads race
         with in-flight kernels); on one box it costs a stream sync."""
-        devices = {h.rdma_buffer.device for h in self._handles.values()}
-        for dev in devices:
+        for dev in self._devices:
             torch.cuda.current_stream(dev).synchronize()
 
     def _drop_plans(self) -> None:
@@ -293,6 +307,8 @@ class DirectWeightSyncDest:
     def __init__(self) -> None:
         self._plan: list[_TransferOp] | None = None
         self._plan_signature: tuple | None = None
+        self._plan_ids: tuple | None = None  # id() of the destination objects the plan was built for
+        self._plan_refs: list | None = None  # ...kept alive, so those ids cannot be recycled
         self._native_plans: dict[int, int] = {}  # device -> plan id
         self.last_pull_ms: dict[int, float] = {}  # device -> kernel time of the last pull
 
@@ -393,37 +409,49 @@ class DirectWeightSyncDest:
                    dest_state_dict: dict[str, torch.Tensor],
                    dest_slices: dict[str, TensorSlice] | None = None) -> None:
         """Pull every overlapping region into ``dest_state_dict`` (in place).  Returns when the
-        bytes are in destination HBM (so the caller may tell the source it is done reading)."""
-        signature = self._signature(dest_state_dict)
-        if self._plan is not None and signature != self._plan_signature:
-            # same object asked to fill different memory: the cached plan would write the old tensors
-            logger.info("destination tensors changed; rebuilding the transfer plan")
-            self.close()
+        bytes are in destination HBM (so the caller may tell the source it is done reading).
+
+        Steady state costs one native call to launch and a poll loop: the cached plan is checked
+        against the destination OBJECTS first (their ids; the plan keeps them alive), the kernel
+        is enqueued, and the data-pointer signature -- which catches ``param.data = new`` under an
+        unchanged object -- is recomputed while the kernel runs."""
+        ids = tuple(map(id, dest_state_dict.values()))
+        verified = False
+        if self._plan is not None and ids != self._plan_ids:
+            # other wrapper objects: fine if they alias the same memory (e.g. a fresh state_dict())
+            if self._signature(dest_state_dict) != self._plan_signature:
+                logger.info("destination tensors changed; rebuilding the transfer plan")
+                self.close()
+            else:
+                self._plan_ids, self._plan_refs = ids, list(dest_state_dict.values())
+            verified = True
         if self._plan is None:
             self._plan = self._build_plan(all_handles, dest_state_dict, dest_slices)
             self._compile()
-            self._plan_signature = signature
-        events = self.launch()
-        for dev, (start, done) in events.items():
-            await wait_event(done)
-            self.last_pull_ms[dev] = start.elapsed_ms(done)
-            start.close()
-            done.close()
+            self._plan_signature = self._signature(dest_state_dict)
+            self._plan_ids, self._plan_refs = ids, list(dest_state_dict.values())
+            verified = True
+        self.launch()
+        stale = not verified and self._signature(dest_state_dict) != self._plan_signature
+        await self.wait()
+        if stale:
+            # the launch above filled the OLD memory (still referenced by the plan, so harmless)
+            logger.info("destination storage changed under the same tensors; rebuilding the transfer plan")
+            self.close()
+            await self.pull(all_handles, dest_state_dict, dest_slices)
 
-    def launch(self) -> dict[int, tuple["_native.Event", "_native.Event"]]:
-        """Enqueue the cached plan on each device's copy stream; returns (start, done) events."""
+    def launch(self) -> None:
+        """Enqueue the cached plan on each device's copy stream, fenced against the caller's current
+        stream on both sides (later work on that stream sees the new weights without a host wait)."""
         if self._plan is None:
             raise RuntimeError("pull() must build the plan first")
-        events = {}
         for dev, plan in self._native_plans.items():
-            _fence_in(dev)
-            start = _native.Event(dev, timing=True).record(None)
-            _native.plan_run(plan, None)
-            done = _native.Event(dev, timing=True).record(None)
-            # later work on the caller's stream sees the new weights even if it does not host-wait
-            done.wait_on(dev, _native.torch_stream(dev))
-            events[dev] = (start, done)
-        return events
+            _native.plan_launch(plan, _native.torch_stream(dev))
+
+    async def wait(self) -> None:
+        for dev, plan in self._native_plans.items():
+            await wait_plan(plan)
+            self.last_pull_ms[dev] = _native.plan_elapsed_ms(plan)
 
     def close(self) -> None:
         for plan in self._native_plans.values():
@@ -433,6 +461,7 @@ class DirectWeightSyncDest:
                 logger.warning("plan_destroy failed: %s", e)
         self._native_plans = {}
         self._plan = None
+        self._plan_ids = self._plan_refs = None
 
 
 def _contig(shape) -> tuple:
