@@ -22,7 +22,7 @@ def build(force: bool = False) -> str:
     stale = (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(hdr))
     if force or stale:
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
-        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-pthread", "-std=c11", "-I", os.path.dirname(hdr), "-o", LIB + ".tmp", src]
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-pthread", "-std=gnu11", "-I", os.path.dirname(hdr), "-o", LIB + ".tmp", src]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
             raise RuntimeError(f"oracle build failed:\n{proc.stdout}\n{proc.stderr}")
@@ -37,6 +37,8 @@ def lib() -> C.CDLL:
         h = C.CDLL(LIB)
         h.oracle_copy_rects.restype = C.c_int
         h.oracle_copy_rects.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+        h.oracle_copy_rects_pinned.restype = C.c_int
+        h.oracle_copy_rects_pinned.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int]
         h.oracle_convert.restype = C.c_int
         h.oracle_convert.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int]
         h.oracle_replay_plan.restype = C.c_int
@@ -45,9 +47,11 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def copy_rects(rects, n: int, nan_mode: int = 0, nthreads: int = 1) -> None:
-    """rects: ctypes array of tsb_rect_t (torchstore_b200._native.Rect) with host pointers."""
-    st = lib().oracle_copy_rects(C.cast(rects, C.c_void_p), n, nan_mode, nthreads)
+def copy_rects(rects, n: int, nan_mode: int = 0, nthreads: int = 1, pin: bool = False) -> None:
+    """rects: ctypes array of tsb_rect_t (torchstore_b200._native.Rect) with host pointers.
+    pin=True binds worker t to the t-th allowed core (stable NUMA placement for bench.py's baseline)."""
+    fn = lib().oracle_copy_rects_pinned if pin else lib().oracle_copy_rects
+    st = fn(C.cast(rects, C.c_void_p), n, nan_mode, nthreads)
     if st != 0:
         raise RuntimeError(f"oracle_copy_rects failed with {st}")
 

@@ -24,7 +24,9 @@
  *
  * Build: see oracle/Makefile (gcc -O2 -shared -fPIC -pthread).
  */
+#define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -194,6 +196,7 @@ typedef struct {
   int tid, nthreads;
   uint64_t total_bytes;
   int status;
+  int cpu; /* >= 0: pin this worker to that core (bench.py's baseline: stable NUMA placement) */
 } job_t;
 
 static uint64_t rect_bytes(const tsb_rect_t* r) {
@@ -206,6 +209,12 @@ static uint64_t rect_bytes(const tsb_rect_t* r) {
  * at::parallel_for splits a big copy_ across intra-op threads. */
 static void* worker(void* arg) {
   job_t* j = (job_t*)arg;
+  if (j->cpu >= 0) {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(j->cpu, &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set); /* best effort */
+  }
   const uint64_t lo = j->total_bytes / (uint64_t)j->nthreads * (uint64_t)j->tid;
   const uint64_t hi = (j->tid == j->nthreads - 1) ? j->total_bytes : j->total_bytes / (uint64_t)j->nthreads * (uint64_t)(j->tid + 1);
   uint64_t pos = 0;
@@ -227,8 +236,21 @@ static void* worker(void* arg) {
   return NULL;
 }
 
+static int copy_rects_impl(const tsb_rect_t* rects, uint64_t n, int nan_mode, int nthreads, int pin);
+
 /* Move every rect.  nthreads <= 1 runs inline.  Returns 0 or -1 (bad descriptor / unsupported cast). */
 int oracle_copy_rects(const tsb_rect_t* rects, uint64_t n, int nan_mode, int nthreads) {
+  return copy_rects_impl(rects, n, nan_mode, nthreads, 0);
+}
+
+/* Same, with worker t pinned to the t-th core of the caller's affinity mask: every worker owns the
+ * same byte range of the same rect list on every call, so after the first touch its pages are
+ * NUMA-local (what a long-lived shm segment + a pinned intra-op pool give the reference). */
+int oracle_copy_rects_pinned(const tsb_rect_t* rects, uint64_t n, int nan_mode, int nthreads) {
+  return copy_rects_impl(rects, n, nan_mode, nthreads, 1);
+}
+
+static int copy_rects_impl(const tsb_rect_t* rects, uint64_t n, int nan_mode, int nthreads, int pin) {
   uint64_t total = 0;
   for (uint64_t i = 0; i < n; ++i) total += rect_bytes(&rects[i]);
   if (nthreads <= 1 || total < (1u << 20)) {
@@ -241,8 +263,15 @@ int oracle_copy_rects(const tsb_rect_t* rects, uint64_t n, int nan_mode, int nth
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256];
   job_t jobs[256];
+  int cpus[1024], ncpu = 0;
+  if (pin) {
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+      for (int c = 0; c < CPU_SETSIZE && ncpu < 1024; ++c)
+        if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+  }
   for (int t = 0; t < nthreads; ++t) {
-    jobs[t] = (job_t){rects, n, nan_mode, t, nthreads, total, 0};
+    jobs[t] = (job_t){rects, n, nan_mode, t, nthreads, total, 0, ncpu ? cpus[t % ncpu] : -1};
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
   int status = 0;

@@ -136,13 +136,13 @@ def test_link_ring_geometries(stage_bytes, stages, monkeypatch):
     def rnd(*shape):
         return torch.randint(-30000, 30000, shape, dtype=torch.int16, device="cuda", generator=g)
 
-    a = rnd(300, 1000)       # rows of 2000 B -> 8-byte units: stays in the copy queue
+    a = rnd(300, 1100)[:, :1004]  # rows of 2008 B, pitch 2200 B -> 8-byte units: stays in the copy queue
     b = rnd(1 << 21)         # one wide row (4 MiB)
     c = rnd(777, 4096)       # narrow 1 KiB windows, source pitch 8 KiB, destination contiguous
     d = rnd(64, 3, 20000)    # wide rows (16 KiB windows of 40 KB rows) under two outer dims
     e = rnd(512, 1792 * 8)   # 3.5 KiB windows into a strided destination
     e_dst = torch.zeros(512, 4096, dtype=torch.int16, device="cuda")
-    outs = [torch.zeros_like(a), torch.zeros_like(b), torch.zeros(777, 512, dtype=torch.int16, device="cuda"),
+    outs = [torch.zeros(300, 1004, dtype=torch.int16, device="cuda"), torch.zeros_like(b), torch.zeros(777, 512, dtype=torch.int16, device="cuda"),
             torch.zeros(64, 3, 8192, dtype=torch.int16, device="cuda")]
     pairs = [(a, outs[0]), (b, outs[1]), (c[:, 1024:1536], outs[2]), (d[:, :, 4096:12288], outs[3]),
              (e[:, 1792:3584], e_dst[:, 1024:2816])]

@@ -443,6 +443,14 @@ def host_free(ptr: int) -> None:
     check(lib().tsb_host_free(C.c_void_p(ptr)))
 
 
+def host_register(ptr: int, nbytes: int) -> None:
+    check(lib().tsb_host_register(C.c_void_p(ptr), nbytes))
+
+
+def host_unregister(ptr: int) -> None:
+    check(lib().tsb_host_unregister(C.c_void_p(ptr)))
+
+
 def memcpy_async(device: int, dst: int, src: int, nbytes: int, kind: int, stream: int | None = None) -> None:
     check(lib().tsb_memcpy_async(device, C.c_void_p(dst), C.c_void_p(src), nbytes, kind,
                                  C.c_void_p(stream) if stream else None))

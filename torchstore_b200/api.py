@@ -57,6 +57,10 @@ async def initialize(num_storage_volumes: int = 1, strategy: TorchStoreStrategy 
         strategy = ControllerStorageVolumes()
     elif strategy is None:
         raise RuntimeError("Must specify controller strategy if num_storage_volumes > 1")
+    if store_name in _controllers or store_name in _spmd_state_map:
+        # refuse BEFORE spawning: registering fresh volumes under the live store's actor names would
+        # replace its data (the reference leaves an initialised store intact, controller.py:118-121)
+        raise RuntimeError(f"TorchStore '{store_name}' is already initialized in this process; call shutdown() first")
     members = _spawn_volumes(num_storage_volumes, strategy, store_name)
     if isinstance(strategy, ControllerStorageVolumes):
         storage_volumes = members[0][1]

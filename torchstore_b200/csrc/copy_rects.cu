@@ -50,12 +50,17 @@ __device__ __forceinline__ void stg16(char* p, const uint4& v) {
 }
 
 // ---- movers: how one unit travels from src to dst ---------------------------------------------
-struct MoveB16 {
-  static constexpr int kUnroll = 4;
+template <int U>
+struct MoveB16T {
+  static constexpr int kUnroll = U;
   using Reg = uint4;
   static __device__ __forceinline__ Reg ld(const char* p) { return ldg16(p); }
   static __device__ __forceinline__ void st(char* p, const Reg& v) { stg16(p, v); }
 };
+using MoveB16 = MoveB16T<4>;
+// Half the loads in flight per thread: used when the launch shares HBM with peers pulling from it
+// (a shallower local queue keeps the latency of the served NVLink reads down)
+using MoveB16Shallow = MoveB16T<2>;
 template <typename T>
 struct MoveSmall {
   static constexpr int kUnroll = 4;
@@ -275,12 +280,17 @@ __device__ __forceinline__ void move_tile(const DevRect& r, uint32_t tile_in_rec
 // KIND selects a kernel specialisation chosen by the plan compiler:
 //   KIND_GENERIC  any mix of modes (per-tile dispatch, out-of-line movers)
 //   KIND_B16      every rect moves 16-byte units: the weight-sync case, fully inlined
+//   KIND_B16_SHALLOW  same, 2 instead of 4 loads in flight per thread
 //   KIND_F32_BF16 every rect is the vector fp32->bf16 cast (transfer_dtype=bf16), fully inlined
 template <int KIND>
 __device__ __forceinline__ void process_tile(const DevRect& r, uint32_t tile_in_rect) {
   const uint32_t tile_units = r.tile_units;
   if (KIND == KIND_B16) {
     move_tile<MoveB16, true>(r, tile_in_rect, tile_units);
+    return;
+  }
+  if (KIND == KIND_B16_SHALLOW) {
+    move_tile<MoveB16Shallow, true>(r, tile_in_rect, tile_units);
     return;
   }
   if (KIND == KIND_F32_BF16) {
@@ -527,10 +537,18 @@ std::atomic<uint64_t> g_launches{0};
 
 template <int KIND>
 cudaError_t prepare_kernel() {
-  // the link ring may exceed the 48 KiB default dynamic shared memory limit
-  static cudaError_t once = cudaFuncSetAttribute(copy_rects_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 static_cast<int>(kMaxLinkStages * 16384));
-  return once;
+  // the link ring plus the static tables exceed the 48 KiB default shared memory limit; function
+  // attributes are per device (context), so set it once on every device the kernel runs on
+  static std::atomic<uint64_t> prepared{0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const uint64_t bit = 1ull << (dev & 63);
+  if (prepared.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(copy_rects_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(kMaxLinkStages * 16384));
+  if (e == cudaSuccess) prepared.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 template <int KIND>
@@ -562,6 +580,7 @@ int max_ctas_per_sm(uint32_t kind, bool with_link, uint32_t link_smem_bytes, int
   const uint32_t smem = with_link ? link_smem_bytes : 0u;
   switch (kind) {
     case KIND_B16: e = occupancy<KIND_B16>(with_link, smem, &n); break;
+    case KIND_B16_SHALLOW: e = occupancy<KIND_B16_SHALLOW>(with_link, smem, &n); break;
     case KIND_F32_BF16: e = occupancy<KIND_F32_BF16>(with_link, smem, &n); break;
     default: e = occupancy<KIND_GENERIC>(with_link, smem, &n); break;
   }
@@ -581,6 +600,7 @@ int launch_copy_rects(const LaunchParams& p, uint32_t grid, cudaStream_t stream)
   cudaError_t e;
   switch (p.kind) {
     case KIND_B16: e = launch<KIND_B16>(p, grid, stream); break;
+    case KIND_B16_SHALLOW: e = launch<KIND_B16_SHALLOW>(p, grid, stream); break;
     case KIND_F32_BF16: e = launch<KIND_F32_BF16>(p, grid, stream); break;
     default: e = launch<KIND_GENERIC>(p, grid, stream); break;
   }

@@ -299,7 +299,8 @@ struct Compiler {
       all_b16 = all_b16 && r.mode == MODE_B16;
       all_cast = all_cast && r.mode == MODE_F32_BF16_V8;
     }
-    return all_b16 ? KIND_B16 : all_cast ? KIND_F32_BF16 : KIND_GENERIC;
+    if (all_b16) return env_u32("TSB_COPY_UNROLL", 4) == 2 ? KIND_B16_SHALLOW : KIND_B16;
+    return all_cast ? KIND_F32_BF16 : KIND_GENERIC;
   }
 
   // Tile order of one queue: proportional interleave over source devices, starting after the

@@ -98,7 +98,7 @@ struct DevTile {
 };
 
 // kernel specialisations (see copy_rects.cu)
-enum : uint32_t { KIND_GENERIC = 0, KIND_B16 = 1, KIND_F32_BF16 = 2 };
+enum : uint32_t { KIND_GENERIC = 0, KIND_B16 = 1, KIND_F32_BF16 = 2, KIND_B16_SHALLOW = 3 };
 
 // Two work queues per plan (see copy_rects.cu):
 //   copy queue  tiles moved by the CTA's 8 copy warps with LDG.128/STG.128 (local HBM sources,

@@ -45,14 +45,14 @@ def endpoint(fn):
     return fn
 
 
-# process-local registry: actor name -> (object, lock)
-_registry: dict[str, tuple[Any, threading.RLock]] = {}
+# process-local registry: actor name -> (object, mailbox lock)
+_registry: dict[str, tuple[Any, threading.Lock]] = {}
 _registry_lock = threading.Lock()
 
 
 def register_actor(name: str, obj: Any) -> "LocalActorRef":
     with _registry_lock:
-        _registry[name] = (obj, threading.RLock())
+        _registry[name] = (obj, threading.Lock())
     return LocalActorRef(name)
 
 
@@ -74,8 +74,18 @@ async def _invoke(name: str, method: str, args, kwargs):
     fn = getattr(obj, method)
     if not getattr(fn, "_tsb_endpoint", False):
         raise ActorError(f"AttributeError: {type(obj).__name__}.{method} is not an endpoint")
-    with lock:
+    # One endpoint at a time per actor (Monarch's mailbox semantics), for callers on ANY thread or
+    # event loop: a plain non-reentrant lock, acquired by yielding to the loop instead of blocking it,
+    # so a coroutine of the same loop that holds the mailbox can finish and other actors keep being
+    # served meanwhile.  (An actor must not call its own endpoints through a ref.)
+    spins = 0
+    while not lock.acquire(blocking=False):
+        spins += 1
+        await asyncio.sleep(0 if spins < 200 else 0.0005)
+    try:
         return await fn(*args, **kwargs)
+    finally:
+        lock.release()
 
 
 class _LocalEndpoint:
@@ -164,9 +174,15 @@ class _RemoteEndpoint:
     async def call_one(self, *args, **kwargs):
         conn, lock = _connections.get(self._ref._address, self._ref._authkey)
         payload = pickle.dumps((self._ref._name, self._method, args, kwargs), protocol=pickle.HIGHEST_PROTOCOL)
-        with lock:
-            conn.send_bytes(payload)
-            ok, out = pickle.loads(conn.recv_bytes())
+
+        def roundtrip():
+            with lock:  # one request/reply in flight per connection
+                conn.send_bytes(payload)
+                return conn.recv_bytes()
+
+        # blocking socket I/O runs on a worker thread: the caller's loop stays live, so
+        # asyncio.gather over several volumes really is concurrent (reference client.py:329-331)
+        ok, out = pickle.loads(await asyncio.get_running_loop().run_in_executor(None, roundtrip))
         if not ok:
             raise ActorError(out)
         return out

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import logging
 import os
+import time
 import weakref
 from dataclasses import dataclass
 from typing import TYPE_CHECKING, Any
@@ -204,6 +205,9 @@ class HbmTransportBuffer(TransportBuffer):
         self._needs_handshake = False
         self._contexts: list[HbmContext] = []
         self._put_specs: list[_PutSpec | None] = []
+        # identifies THIS put on the volume between handshake and put (two clients may put the same
+        # key concurrently; each must get back the landing buffer it wrote into)
+        self._nonce = os.urandom(8).hex()
 
     def __getstate__(self) -> dict[str, Any]:
         state = self.__dict__.copy()
@@ -227,7 +231,9 @@ class HbmTransportBuffer(TransportBuffer):
         """Volume: hand out where each tensor must be written."""
         vol = ctx.get(HbmVolumeCache)
         out: list[HbmDescriptor | None] = []
-        for (request, current), spec in zip(entries, self._put_specs, strict=True):
+        pending = _pending(ctx)
+        _purge_stale(pending)
+        for idx, ((request, current), spec) in enumerate(zip(entries, self._put_specs, strict=True)):
             if spec is None:
                 out.append(None)
                 continue
@@ -237,7 +243,7 @@ class HbmTransportBuffer(TransportBuffer):
             else:
                 target = vol.allocate(spec.shape, spec.dtype)
             # keep new allocations alive until handle_put_request stores them
-            _pending(ctx)[(request.key, _coords(request))] = target
+            pending[(self._nonce, idx)] = (time.monotonic(), target)
             out.append(HbmDescriptor.from_tensor(target))
         return out
 
@@ -285,13 +291,13 @@ class HbmTransportBuffer(TransportBuffer):
     async def handle_put_request(self, ctx: "TransportContext", entries: list[tuple[Request, Any]]) -> list[Any]:
         results = []
         pending = _pending(ctx)
-        for (request, current), hctx in zip(entries, self._contexts, strict=True):
+        for idx, ((request, current), hctx) in enumerate(zip(entries, self._contexts, strict=True)):
             if hctx.use_rpc:
                 results.append(hctx.objects)
                 continue
-            target = pending.pop((request.key, _coords(request)), None)
-            assert target is not None, f"No landing buffer for {request.key}; handshake and put raced"
-            results.append(target)
+            entry = pending.pop((self._nonce, idx), None)
+            assert entry is not None, f"No landing buffer for {request.key}: put without a matching handshake"
+            results.append(entry[1])
         return results
 
     # ---- GET ------------------------------------------------------------------------------------
@@ -361,7 +367,13 @@ class HbmTransportBuffer(TransportBuffer):
                 src_ptr = bounce.data_ptr()
             else:
                 bounce, src_ptr = None, src.ptr
-            host = dest if (dest is not None and dest.is_contiguous()) else torch.empty(desc.shape, dtype=desc.dtype)
+            # raw stored bytes may only land in a host tensor of the SAME dtype and size; anything else
+            # goes through a temporary and a converting copy_ (what the reference's
+            # client_tensor.copy_(shm_tensor) does, shared_memory.py:473-476) -- never a memcpy of
+            # desc.nbytes into a buffer of another size
+            direct = dest is not None and dest.is_contiguous() and dest.dtype == desc.dtype and \
+                dest.numel() * dest.element_size() == desc.nbytes
+            host = dest if direct else torch.empty(desc.shape, dtype=desc.dtype)
             _native.memcpy_async(dev, host.data_ptr(), src_ptr, desc.nbytes, _native.TSB_D2H)
             devices.add(dev)
             staged.append((i, dest, host, bounce))
@@ -388,8 +400,17 @@ def _pending(ctx: "TransportContext") -> dict:
     return vol._pending
 
 
-def _coords(request: Request):
-    return None if request.tensor_slice is None else request.tensor_slice.coordinates
+_PENDING_TTL_S = 300.0
+
+
+def _purge_stale(pending: dict) -> None:
+    """Landing buffers of puts that failed between handshake and put (the client's drop() cannot
+    reach the volume) go back to the arena after a grace period."""
+    if not pending:
+        return
+    now = time.monotonic()
+    for k in [k for k, (t, _) in pending.items() if now - t > _PENDING_TTL_S]:
+        pending.pop(k, None)
 
 
 def _same_process(desc: HbmDescriptor) -> bool:
