@@ -86,6 +86,10 @@ typedef struct tsb_region {
   int32_t device;         /* CUDA ordinal in the exporting process */
   int32_t pid;            /* exporting process */
   uint64_t boot_id;       /* random per-library-load id: disambiguates recycled pids */
+  uint64_t epoch;         /* driver-unique id of the enclosing allocation (CU_POINTER_ATTRIBUTE_BUFFER_ID):
+                           * a different epoch at the same exporter address means the old allocation was
+                           * freed and the address reused -> importers drop the stale mapping
+                           * (registration-cache eviction, transport/torchcomms/cache.py:150-186) */
 } tsb_region_t;
 
 /* Describe [ptr, ptr+nbytes) so another process/GPU can map it.  Works on any cudaMalloc-backed
@@ -101,6 +105,9 @@ int tsb_import_region(const tsb_region_t* region, int device, void** out_ptr);
 int tsb_release_region(const tsb_region_t* region);
 /* Drop every cached mapping (== TransportContext.clear()). */
 int tsb_release_all(void);
+/* Import-cache counters: live mappings, and mappings evicted because the exporter re-used the
+ * address range for a new allocation (epoch changed). */
+int tsb_import_stats(uint64_t* out_live, uint64_t* out_stale_evictions);
 
 /* ------------------------------------------------------------------------------------------ */
 /* the hot path: batched N-D rectangle gather with optional fused dtype cast                   */
@@ -165,6 +172,11 @@ int tsb_plan_run(tsb_plan_t plan, void* stream);
  * -> start event -> kernel -> done event -> [caller_stream waits for the done event].  The events
  * belong to the plan and are reused.  caller_stream == NULL skips both fences. */
 int tsb_plan_launch(tsb_plan_t plan, void* caller_stream);
+/* Same with flags: TSB_LAUNCH_NO_FENCE_OUT leaves caller_stream free to run ahead of the copy (a put
+ * that overlaps the actor's compute: the caller only promises not to overwrite the sources until it
+ * has observed completion with tsb_plan_poll / tsb_plan_wait). */
+enum { TSB_LAUNCH_DEFAULT = 0, TSB_LAUNCH_NO_FENCE_OUT = 1 };
+int tsb_plan_launch_flags(tsb_plan_t plan, void* caller_stream, uint32_t flags);
 /* Completion of the last tsb_plan_launch: 1 = bytes are in destination HBM, 0 = still running
  * (the await point of `await asyncio.gather(*reads)`, direct_weight_sync.py:338-340). */
 int tsb_plan_poll(tsb_plan_t plan, int* out_done);

@@ -31,7 +31,7 @@ def test_abi_version_and_struct_sizes():
     import ctypes as C
 
     assert _native.lib().tsb_abi_version() == _native.TSB_ABI_VERSION
-    assert C.sizeof(_native.Region) == 64 + 8 * 4 + 4 * 2 + 8
+    assert C.sizeof(_native.Region) == 64 + 8 * 4 + 4 * 2 + 8 + 8
     assert C.sizeof(_native.Rect) == 16 + 3 * 6 * 8 + 16
     assert C.sizeof(_native.PlanInfo) == 7 * 8 + 6 * 4
 

@@ -13,6 +13,7 @@ import pytest
 import torch
 
 import torchstore_b200 as ts
+from torchstore_b200 import _native
 from oracle import reshard_oracle as ro
 from torchstore_b200.transport import create_transport_buffer
 from torchstore_b200.transport.types import Request, TensorSlice
@@ -251,6 +252,102 @@ def test_volume_memory_is_hbm_arena_and_freed_on_delete():
 
             gc.collect()
             assert vol.store.stats()["in_use"] == 0
+        finally:
+            await ts.shutdown()
+
+    run(main())
+
+
+def test_fast_lane_replays_put_and_get_and_invalidates_on_layout_change():
+    """Store-path fast lane: an identical put_batch / in-place get_batch replays its compiled plan
+    (no handshake, no per-key RPC payload); any change of the volume layout (delete, reallocation)
+    or of the index drops the session and the slow path takes over -- results stay bit-exact."""
+    from torchstore_b200.transport.hbm import HbmClientCache
+
+    async def main():
+        await ts.initialize()
+        try:
+            cl = await ts.client()
+            cache = cl.strategy.transport_context.get(HbmClientCache)
+            src = {f"w{i}": torch.randn(257, 129, device=DEV) for i in range(6)}
+            dst = {k: torch.zeros_like(v) for k, v in src.items()}
+            await ts.put_batch(src)                       # slow path, records a session
+            assert cache.misses == 1 and cache.hits == 0 and len(cache.put_sessions) == 1
+            before = _native.launch_count()
+            for k in src:
+                src[k].add_(1.0)
+            await ts.put_batch(src)                       # replay
+            assert cache.hits == 1 and _native.launch_count() == before + 1
+            await ts.get_batch(dst)                       # slow get, records
+            assert all(torch.equal(dst[k], src[k]) for k in src) and cl.get_session_hits == 0
+            for k in src:
+                src[k].mul_(-2.0)
+            await ts.put_batch(src)
+            out = await ts.get_batch(dst)                 # replayed get: one launch, returns the caller's objects
+            assert cl.get_session_hits == 1 and all(out[k] is dst[k] for k in dst)
+            assert all(torch.equal(dst[k], src[k]) for k in src)
+            # a different destination set is a different session (not a false hit)
+            dst2 = {k: torch.zeros_like(v) for k, v in src.items()}
+            await ts.get_batch(dst2)
+            assert cl.get_session_hits == 1 and all(torch.equal(dst2[k], src[k]) for k in src)
+            # layout change: delete one key, put it back with another shape -> sessions are stale
+            await ts.delete("w0")
+            with pytest.raises(Exception):
+                await ts.get_batch(dst)                   # w0 is gone: the replay must NOT serve stale bytes
+            src["w0"] = torch.randn(300, 10, device=DEV)
+            dst["w0"] = torch.zeros(300, 10, device=DEV)
+            await ts.put_batch(src)                       # new signature + stale old session
+            await ts.get_batch(dst)
+            assert all(torch.equal(dst[k], src[k]) for k in src)
+            hits = cache.hits
+            await ts.put_batch(src)                       # and the new batch replays again
+            assert cache.hits == hits + 1
+            # same keys, same shapes, but the volume reallocated (dtype change) -> epoch moved
+            src["w1"] = src["w1"].to(torch.float16)
+            await ts.put_batch(src)
+            got = await ts.get("w1")
+            assert got.dtype == torch.float16 and torch.equal(got, src["w1"].cpu())
+        finally:
+            await ts.shutdown()
+
+    run(main())
+
+
+def test_put_batch_wait_false_overlaps_and_completes():
+    async def main():
+        await ts.initialize()
+        try:
+            src = {"a": torch.randn(1 << 22, device=DEV), "b": torch.randn(1 << 20, device=DEV)}
+            first = await ts.put_batch(src, wait=False)   # first put: completes inline
+            assert first.done
+            src["a"].add_(3.0)
+            pending = await ts.put_batch(src, wait=False)  # replayed: returns with the copy in flight
+            marker = torch.ones(1 << 20, device=DEV).sum()  # caller's compute is not fenced behind the copy
+            await pending
+            assert pending.done and float(marker) == float(1 << 20)
+            dst = {k: torch.zeros_like(v) for k, v in src.items()}
+            await ts.get_batch(dst)
+            assert torch.equal(dst["a"], src["a"]) and torch.equal(dst["b"], src["b"])
+        finally:
+            await ts.shutdown()
+
+    run(main())
+
+
+def test_host_destination_of_other_dtype_is_converted_not_overrun():
+    """stored fp32, caller hands a bf16 / fp64 CPU tensor of the same shape: the raw bytes
+    must go through a converting copy (like the reference's copy_), never a memcpy of the stored size."""
+    async def main():
+        await ts.initialize()
+        try:
+            x = torch.randn(1000, 37, device=DEV)
+            await ts.put("x", x)
+            for dt in (torch.bfloat16, torch.float64, torch.float32):
+                guard = torch.full((1000 * 37 + 64,), 7.0, dtype=dt)
+                dest = guard[:1000 * 37].view(1000, 37)
+                out = await ts.get("x", dest)
+                assert out is dest and torch.equal(dest, x.cpu().to(dt))
+                assert bool((guard[1000 * 37:] == 7.0).all())  # nothing written past the destination
         finally:
             await ts.shutdown()
 

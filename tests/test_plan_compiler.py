@@ -79,14 +79,14 @@ def test_tile_order_interleaves_sources_and_covers_everything(monkeypatch):
     # NO_INTERLEAVE keeps rect order
     _, tiles2, _ = _native.plan_compile_host(0, rects, n, _native.TSB_PLAN_NO_INTERLEAVE, 256)
     assert tiles2[:, 0].tolist() == sorted(tiles2[:, 0].tolist())
-    # default: NVLink sources ride the link queue -- 8 KiB tiles, rotated in granules of 8 (one claim)
+    # default: NVLink sources ride the link queue -- 4 KiB tiles, rotated in granules of 8 (one claim)
     monkeypatch.delenv("TSB_LINK")
     dst.zero_()
     table, tiles, info = _native.plan_compile_host(0, rects, n, 0, 256)
-    assert info.num_tiles == 0 and info.num_link_tiles == 3 * 32 and info.link_bytes == info.remote_src_bytes
+    assert info.num_tiles == 0 and info.num_link_tiles == 3 * 64 and info.link_bytes == info.remote_src_bytes
     assert info.block == 256 + 32
     assert tiles[:, 0].tolist()[:32] == [0] * 8 + [1] * 8 + [2] * 8 + [0] * 8
-    assert len(set(map(tuple, tiles.tolist()))) == 3 * 32
+    assert len(set(map(tuple, tiles.tolist()))) == 3 * 64
     c_oracle.replay_plan(table, tiles, 256)
     for i in range(3):
         assert torch.equal(dst[i], src[i])

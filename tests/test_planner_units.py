@@ -76,7 +76,7 @@ def test_span_and_region_blob_roundtrip():
     reg.offset, reg.nbytes, reg.device, reg.pid, reg.boot_id = 4096, 1234, 3, 77, 0xDEADBEEF
     back = _native.region_from_bytes(_native.region_to_bytes(reg))
     assert (back.offset, back.nbytes, back.device, back.pid, back.boot_id) == (4096, 1234, 3, 77, 0xDEADBEEF)
-    assert C.sizeof(back) == 112
+    assert C.sizeof(back) == 120
     with pytest.raises(ValueError):
         _native.region_from_bytes(b"short")
 

@@ -25,6 +25,17 @@ pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="r
 import workloads  # noqa: E402
 
 
+@pytest.fixture(autouse=True)
+def _restore_sys_path():
+    """import_reference() puts /root/reference first on sys.path; it has its own ``tests`` package,
+    which must not shadow ours in processes spawned by later tests."""
+    import sys
+
+    saved = list(sys.path)
+    yield
+    sys.path[:] = saved
+
+
 def _fake_buffer(shape, dtype, device):
     """An NvlinkBuffer as a destination process sees it after unpickling: descriptor only."""
     stride = []
@@ -32,7 +43,7 @@ def _fake_buffer(shape, dtype, device):
     for e in reversed(shape):
         stride.append(s)
         s *= e
-    desc = HbmDescriptor(region=bytes(112), shape=tuple(shape), stride=tuple(reversed(stride)), dtype=dtype, device=device)
+    desc = HbmDescriptor(region=bytes(120), shape=tuple(shape), stride=tuple(reversed(stride)), dtype=dtype, device=device)
     return ours.NvlinkBuffer(descriptor=desc)
 
 

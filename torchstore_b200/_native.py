@@ -43,6 +43,7 @@ class Region(C.Structure):
         ("device", C.c_int32),
         ("pid", C.c_int32),
         ("boot_id", C.c_uint64),
+        ("epoch", C.c_uint64),
     ]
 
 
@@ -107,11 +108,13 @@ _SIGNATURES = {
     "tsb_import_region": (C.c_int, [C.POINTER(Region), C.c_int, C.POINTER(_vp)]),
     "tsb_release_region": (C.c_int, [C.POINTER(Region)]),
     "tsb_release_all": (C.c_int, []),
+    "tsb_import_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tsb_cast_supported": (C.c_int, [C.c_uint32, C.c_uint32]),
     "tsb_plan_create": (C.c_int, [C.c_int, C.POINTER(Rect), C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "tsb_plan_info": (C.c_int, [C.c_uint64, C.POINTER(PlanInfo)]),
     "tsb_plan_run": (C.c_int, [C.c_uint64, _vp]),
     "tsb_plan_launch": (C.c_int, [C.c_uint64, _vp]),
+    "tsb_plan_launch_flags": (C.c_int, [C.c_uint64, _vp, C.c_uint32]),
     "tsb_plan_poll": (C.c_int, [C.c_uint64, C.POINTER(C.c_int)]),
     "tsb_plan_wait": (C.c_int, [C.c_uint64]),
     "tsb_plan_elapsed_ms": (C.c_int, [C.c_uint64, C.POINTER(C.c_float)]),
@@ -259,6 +262,12 @@ def release_all() -> None:
     check(lib().tsb_release_all())
 
 
+def import_stats() -> dict:
+    live, stale = C.c_uint64(0), C.c_uint64(0)
+    check(lib().tsb_import_stats(C.byref(live), C.byref(stale)))
+    return {"live": live.value, "stale_evictions": stale.value}
+
+
 def region_to_bytes(region: Region) -> bytes:
     return bytes(region)
 
@@ -289,9 +298,14 @@ def plan_run(plan: int, stream: int | None = None) -> None:
     check(lib().tsb_plan_run(plan, C.c_void_p(stream) if stream else None))
 
 
-def plan_launch(plan: int, caller_stream: int | None = None) -> None:
-    """fence-in, start event, kernel, done event, fence-out: one native call per sync."""
-    check(lib().tsb_plan_launch(plan, C.c_void_p(caller_stream) if caller_stream else None))
+TSB_LAUNCH_NO_FENCE_OUT = 1
+
+
+def plan_launch(plan: int, caller_stream: int | None = None, fence_out: bool = True) -> None:
+    """fence-in, start event, kernel, done event, fence-out: one native call per sync.
+    ``fence_out=False``: the caller's stream is not made to wait for the copy (overlapping puts)."""
+    check(lib().tsb_plan_launch_flags(plan, C.c_void_p(caller_stream) if caller_stream else None,
+                                      0 if fence_out else TSB_LAUNCH_NO_FENCE_OUT))
 
 
 _poll_flag = C.c_int(0)

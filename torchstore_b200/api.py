@@ -83,6 +83,7 @@ async def shutdown(store_name: str = DEFAULT_TORCHSTORE_NAME) -> None:
         cl = _local_clent_map.get(store_name)
         if cl is not None:
             state_dict_utils.reset_direct_cache(cl)
+            cl.close_sessions()
             cl.strategy.transport_context.clear()
         reset_client(store_name)
         for name in _owned_actors.pop(store_name, []):
@@ -122,8 +123,10 @@ async def put(key: str, value: torch.Tensor | Any, store_name: str = DEFAULT_TOR
     return await (await client(store_name)).put(key, value)
 
 
-async def put_batch(entries: dict[str, torch.Tensor | Any], store_name: str = DEFAULT_TORCHSTORE_NAME) -> None:
-    return await (await client(store_name)).put_batch(entries)
+async def put_batch(entries: dict[str, torch.Tensor | Any], store_name: str = DEFAULT_TORCHSTORE_NAME, wait: bool = True):
+    """``wait=False`` (extension of the reference signature): returns a PendingPut once the copy is
+    enqueued on the volume's side stream -- it overlaps the caller's compute; ``await`` it to finish."""
+    return await (await client(store_name)).put_batch(entries, wait=wait)
 
 
 async def get(key: str, inplace_tensor: torch.Tensor | None = None, tensor_slice_spec: TensorSlice | None = None,

@@ -10,7 +10,9 @@ destination the bounding box is gathered on the GPU first and moved to the host 
 from __future__ import annotations
 
 import asyncio
+import collections
 from collections import defaultdict
+from dataclasses import dataclass
 from logging import getLogger
 from typing import Any
 
@@ -50,10 +52,43 @@ class GatherTarget:
         return self.tensor[idx]
 
 
+class PendingPut:
+    """Returned by ``put_batch(..., wait=False)``: the copy is running on the side stream; awaiting
+    the object completes the put (data committed and readable by any client).  The caller must not
+    overwrite the source tensors before that."""
+
+    def __init__(self, finish=None) -> None:
+        self._finish = finish
+        self.done = finish is None
+
+    def __await__(self):
+        return self.wait().__await__()
+
+    async def wait(self) -> None:
+        if not self.done:
+            await self._finish()
+            self.done = True
+
+
+@dataclass
+class _GetSession:
+    """A replayable in-place get_batch: per-volume transport sessions plus the controller epoch the
+    volume map was read under (see HbmSession)."""
+
+    controller_epoch: int
+    parts: list  # HbmSession per volume
+    final: dict  # key -> the caller's destination object
+
+
 class LocalClient:
+    MAX_GET_SESSIONS = 64
+
     def __init__(self, controller, strategy) -> None:
         self._controller = controller
         self.strategy: TorchStoreStrategy = strategy
+        self._get_sessions: "collections.OrderedDict[tuple, _GetSession]" = collections.OrderedDict()
+        self._recordings: dict = {}  # signature of a get being recorded -> (controller epoch, transports)
+        self.get_session_hits = 0
 
     async def _locate_volumes(self, keys: list[str]):
         try:
@@ -69,7 +104,11 @@ class LocalClient:
         tracker.track_e2e()
 
     @torch.no_grad
-    async def put_batch(self, entries: dict[str, torch.Tensor | Any]):
+    async def put_batch(self, entries: dict[str, torch.Tensor | Any], wait: bool = True):
+        """``wait=False`` (extension): return a :class:`PendingPut` as soon as the copy has been
+        enqueued on the side stream, so it overlaps the caller's compute; ``await`` it to complete
+        the put.  Only a batch served by the fast lane (put before, nothing moved) can return early;
+        a first put completes inline and returns an already-finished PendingPut."""
         assert isinstance(entries, dict) and entries, "put_batch requires a non-empty dict"
         tracker = LatencyTracker("put_batch")
         requests = [
@@ -79,11 +118,19 @@ class LocalClient:
         volume_ref = self.strategy.select_storage_volume()
         transport = create_transport_buffer(volume_ref)
         tracker.track_step("create transport buffer")
-        await transport.put_to_storage_volume(requests)
+        if getattr(transport, "supports_fast_lane", False):
+            inflight = await transport.put_to_storage_volume(requests, wait=wait)
+        else:
+            inflight = await transport.put_to_storage_volume(requests)
         tracker.track_step("put_to_storage_volume")
-        await self._controller.notify_put_batch.call([r.meta_only() for r in requests], volume_ref.volume_id)
-        tracker.track_step("notify_put_batch")
+        if not getattr(transport, "fast_path_hit", False):
+            # a replayed batch overwrote indexed keys in place: the index is already right
+            await self._controller.notify_put_batch.call([r.meta_only() for r in requests], volume_ref.volume_id)
+            tracker.track_step("notify_put_batch")
         tracker.track_e2e()
+        if not wait:
+            return PendingPut(inflight.wait if inflight is not None else None)
+        return None
 
     # ---- get ------------------------------------------------------------------------------------
     @torch.no_grad
@@ -112,11 +159,81 @@ class LocalClient:
         else:
             raise TypeError(f"get_batch expects list[str] or dict, got {type(keys)}")
         requests = [Request.from_any(k, inplace.get(k)) for k in keys]
-        results = await self._fetch(requests)
+        sig = self._get_signature(requests)
+        if sig is not None:
+            replay = await self._replay_get(sig)
+            if replay is not None:
+                tracker.track_e2e()
+                return replay
+        results = await self._fetch(requests, record_sig=sig)
         tracker.track_step("fetch")
         final = {r.key: self._apply_inplace(results[r.key], inplace.get(r.key), r) for r in requests}
+        self._finish_get_session(sig, requests, results, final)
         tracker.track_e2e()
         return final
+
+    # ---- get fast lane ---------------------------------------------------------------------------
+    def _get_signature(self, requests: list[Request]):
+        """Identity of an in-place get batch (keys, wanted slices, destination memory); None when a
+        request has no GPU destination (nothing to replay into)."""
+        import os
+
+        if os.environ.get("TORCHSTORE_B200_FAST_LANE", "1") != "1":
+            return None
+        sig = []
+        for r in requests:
+            t = r.tensor_val
+            if t is None or not t.is_cuda:
+                return None
+            sig.append((r.key, r.tensor_slice, t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype))
+        return tuple(sig)
+
+    async def _replay_get(self, sig):
+        sess = self._get_sessions.get(sig)
+        if sess is None:
+            return None
+        checks = [self._controller.get_epoch.call_one()] + [p.valid() for p in sess.parts]
+        got = await asyncio.gather(*checks)
+        if got[0] != sess.controller_epoch or not all(got[1:]):
+            self._drop_get_session(sig)
+            return None
+        self._get_sessions.move_to_end(sig)
+        for p in sess.parts:
+            p.launch()
+        for p in sess.parts:
+            await p.wait()
+        self.get_session_hits += 1
+        return dict(sess.final)
+
+    def _drop_get_session(self, sig) -> None:
+        sess = self._get_sessions.pop(sig, None)
+        if sess is not None:
+            for p in sess.parts:
+                p.close()
+
+    def _finish_get_session(self, sig, requests, results, final) -> None:
+        """Keep what a recorded fetch produced if (and only if) every result landed in place."""
+        recorded = self._recordings.pop(sig, None) if sig is not None else None
+        if recorded is None:
+            return
+        epoch, transports = recorded
+        parts = [t.take_session() for t in transports]
+        inplace_ok = all(results[r.key] is not None and isinstance(results[r.key], torch.Tensor)
+                         and results[r.key].data_ptr() == r.tensor_val.data_ptr() for r in requests)
+        if epoch is None or not inplace_ok or any(p is None for p in parts):
+            for p in parts:
+                if p is not None:
+                    p.close()
+            return
+        self._drop_get_session(sig)
+        self._get_sessions[sig] = _GetSession(epoch, parts, dict(final))
+        while len(self._get_sessions) > self.MAX_GET_SESSIONS:
+            old, _ = next(iter(self._get_sessions.items()))
+            self._drop_get_session(old)
+
+    def close_sessions(self) -> None:
+        for sig in list(self._get_sessions):
+            self._drop_get_session(sig)
 
     def _apply_inplace(self, fetched: Any, inplace_tensor, request: Request) -> Any:
         """Always hand back the caller's object; copy only if the fetch could not land in place."""
@@ -125,11 +242,24 @@ class LocalClient:
             return inplace_tensor
         return inplace_tensor if inplace_tensor is not None else fetched
 
-    async def _fetch(self, requests: list[Request]) -> dict[str, Any]:
+    async def _fetch(self, requests: list[Request], record_sig=None) -> dict[str, Any]:
+        epoch = None
+        if record_sig is not None:
+            # read BEFORE the volume map: if the index changes in between, the session is born stale
+            # (and is dropped on its first replay) rather than wrongly valid
+            try:
+                epoch = await self._controller.get_epoch.call_one()
+            except Exception:
+                record_sig = None
         volume_maps = await self._locate_volumes([r.key for r in requests])
         volume_ids = {vid for vm in volume_maps.values() for vid in vm}
         transports = {vid: create_transport_buffer(self.strategy.get_storage_volume(vid)) for vid in volume_ids}
         volume_requests, whole_keys, gathers = self._build_volume_requests(requests, volume_maps, transports)
+        used = [transports[v] for v in volume_requests]
+        if record_sig is not None and all(getattr(t, "supports_fast_lane", False) for t in used):
+            for t in used:
+                t._record = True
+            self._recordings[record_sig] = (epoch, used)
         pairs = await self._fetch_results(volume_requests, transports)
         return await self._assemble_results(requests, pairs, whole_keys, gathers)
 

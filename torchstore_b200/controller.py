@@ -58,6 +58,9 @@ class Controller(Actor):
         self.strategy: TorchStoreStrategy | None = None
         self.storage_volumes = None
         self.num_storage_volumes: int | None = None
+        # bumped whenever the index changes SHAPE (new key / volume / slice, any delete); overwriting
+        # an indexed key in place leaves it alone.  Clients validate cached get plans against it.
+        self.epoch = 0
 
     def assert_initialized(self) -> None:
         assert self.is_initialized, "Please call torchstore.initialize before attempting to use store."
@@ -127,14 +130,23 @@ class Controller(Actor):
         volume_map = self.keys_to_storage_volumes.setdefault(request.key, {})
         info = StorageInfo(ObjectType.from_request(request), {request.tensor_slice})
         if storage_volume_id in volume_map:
-            volume_map[storage_volume_id].update(info)
+            known = volume_map[storage_volume_id]
+            if request.tensor_slice not in known.tensor_slices:
+                self.epoch += 1
+            known.update(info)
         else:
             volume_map[storage_volume_id] = info
+            self.epoch += 1
+
+    @endpoint
+    async def get_epoch(self) -> int:
+        return self.epoch
 
     @endpoint
     async def teardown(self) -> None:
         self.is_initialized = False
         self.keys_to_storage_volumes = KeyIndex()
+        self.epoch += 1
         self.strategy = None
         if self.storage_volumes is not None:
             await self.storage_volumes.reset.call()
@@ -163,6 +175,7 @@ class Controller(Actor):
                 return
             raise KeyError(f"Unable to locate {key} in storage volume {storage_volume_id}.")
         del volume_map[storage_volume_id]
+        self.epoch += 1
         if not volume_map:
             del self.keys_to_storage_volumes[key]
 

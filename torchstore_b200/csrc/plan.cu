@@ -116,8 +116,11 @@ constexpr uint64_t kMaxUnitsPerRow = 1ull << 30;
 
 struct Tuning {
   uint32_t tile_units = 4096;       // copy queue: 64 KiB tiles
-  uint32_t link_tile_units = 512;   // link queue: one 8 KiB ring stage per tile
-  uint32_t link_stages = 6;
+  // link queue: one ring stage per tile.  3 stages x 4 KiB (8 KiB of loads in flight per CTA, 3.5 MB
+  // per GPU) measured best on the 2-GPU emulation of the FSDP(8/4/2)->TP syncs: deeper rings only
+  // lengthen the queues at the source GPU, whose HBM is busy with its own copy (profiles/r2_sweep_x2_*)
+  uint32_t link_tile_units = 256;
+  uint32_t link_stages = 3;
   bool link = true;
   bool link_all = false;  // TSB_LINK=2: local sources too (exercises the link warp on one GPU)
 };
@@ -133,10 +136,10 @@ Tuning default_tuning() {
   Tuning t;
   uint32_t bytes = env_u32("TSB_TILE_BYTES", 65536);
   t.tile_units = std::min<uint32_t>(32768u, std::max<uint32_t>(64u, bytes / 16));
-  uint32_t sb = env_u32("TSB_LINK_STAGE_BYTES", 8192);
+  uint32_t sb = env_u32("TSB_LINK_STAGE_BYTES", 4096);
   sb = std::min<uint32_t>(16384u, std::max<uint32_t>(1024u, sb)) / 16 * 16;
   t.link_tile_units = sb / 16;
-  t.link_stages = std::min<uint32_t>(8u, std::max<uint32_t>(3u, env_u32("TSB_LINK_STAGES", 6)));
+  t.link_stages = std::min<uint32_t>(8u, std::max<uint32_t>(3u, env_u32("TSB_LINK_STAGES", 3)));
   const uint32_t lk = env_u32("TSB_LINK", 1);
   t.link = lk != 0;
   t.link_all = lk == 2;
@@ -660,7 +663,9 @@ int tsb_plan_run(tsb_plan_t plan, void* stream) {
 }
 
 // One call per sync: [caller stream -> fence] start, kernel, done [-> caller stream waits].
-int tsb_plan_launch(tsb_plan_t plan, void* caller_stream) {
+int tsb_plan_launch(tsb_plan_t plan, void* caller_stream) { return tsb_plan_launch_flags(plan, caller_stream, TSB_LAUNCH_DEFAULT); }
+
+int tsb_plan_launch_flags(tsb_plan_t plan, void* caller_stream, uint32_t flags) {
   Plan* p;
   int st = find_plan(plan, &p);
   if (st) return st;
@@ -683,7 +688,7 @@ int tsb_plan_launch(tsb_plan_t plan, void* caller_stream) {
     if ((st = run_plan(p, s))) return st;
   }
   TSB_CUDA(cudaEventRecord(p->ev_done, s));
-  if (cs) TSB_CUDA(cudaStreamWaitEvent(cs, p->ev_done, 0));
+  if (cs && !(flags & TSB_LAUNCH_NO_FENCE_OUT)) TSB_CUDA(cudaStreamWaitEvent(cs, p->ev_done, 0));
   p->launched = true;
   return TSB_OK;
 }

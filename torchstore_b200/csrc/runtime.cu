@@ -87,6 +87,8 @@ struct DeviceState {
 struct ImportEntry {
   void* base = nullptr;  // mapped base of the exporter's allocation
   int opened_on = -1;
+  uint64_t epoch = 0;
+  std::array<uint64_t, 3> where{};  // (boot_id, exporter device, exporter base address)
 };
 
 struct Arena {
@@ -108,6 +110,10 @@ struct Global {
   DeviceState dev[kMaxDevices];
   std::set<std::pair<int, int>> peers;  // (device, peer) enabled by us or already enabled
   std::map<std::array<uint8_t, 72>, ImportEntry> imports;  // boot_id(8) + handle(64)
+  // (boot_id, exporter device, exporter base address) -> key in `imports`: one live allocation per
+  // address, so a second handle for the same address means the first allocation is gone
+  std::map<std::array<uint64_t, 3>, std::array<uint8_t, 72>> import_by_address;
+  uint64_t stale_evictions = 0;
   std::unordered_map<uint64_t, Arena*> arenas;
   uint64_t next_id = 1;
 };
@@ -291,6 +297,10 @@ int tsb_export_region(const void* ptr, uint64_t nbytes, tsb_region_t* out) {
   out->device = attr.device;
   out->pid = static_cast<int32_t>(getpid());
   out->boot_id = g.boot_id;
+  if (p_attr) {
+    unsigned long long id = 0;
+    if (p_attr(&id, CU_POINTER_ATTRIBUTE_BUFFER_ID, base) == CUDA_SUCCESS) out->epoch = id;
+  }
 
   int legacy_ok = 1;
   if (p_attr) {
@@ -347,6 +357,20 @@ int tsb_import_region(const tsb_region_t* region, int device, void** out_ptr) {
   if (it == g.imports.end()) {
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(guard.err, "cudaSetDevice");
+    const std::array<uint64_t, 3> where{region->boot_id, static_cast<uint64_t>(region->device), region->local_ptr - region->offset};
+    auto old = g.import_by_address.find(where);
+    if (old != g.import_by_address.end()) {
+      // the exporter freed the allocation we mapped and its address now belongs to a new one
+      // (new handle, new epoch): the old mapping only pins dead memory -- drop it
+      auto stale = g.imports.find(old->second);
+      if (stale != g.imports.end()) {
+        DeviceGuard g2(stale->second.opened_on);
+        if (cudaIpcCloseMemHandle(stale->second.base) != cudaSuccess) cudaGetLastError();
+        g.imports.erase(stale);
+        ++g.stale_evictions;
+      }
+      g.import_by_address.erase(old);
+    }
     cudaIpcMemHandle_t h;
     memcpy(&h, region->ipc_handle, 64);
     void* base = nullptr;
@@ -355,7 +379,10 @@ int tsb_import_region(const tsb_region_t* region, int device, void** out_ptr) {
     ImportEntry ent;
     ent.base = base;
     ent.opened_on = device;
+    ent.epoch = region->epoch;
+    ent.where = where;
     it = g.imports.emplace(key, ent).first;
+    g.import_by_address[where] = key;
   }
   *out_ptr = static_cast<char*>(it->second.base) + region->offset;
   return TSB_OK;
@@ -374,8 +401,17 @@ int tsb_release_region(const tsb_region_t* region) {
   if (it == g.imports.end()) return TSB_OK;
   DeviceGuard guard(it->second.opened_on);
   cudaError_t e = cudaIpcCloseMemHandle(it->second.base);
+  g.import_by_address.erase(it->second.where);
   g.imports.erase(it);
   if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+  return TSB_OK;
+}
+
+int tsb_import_stats(uint64_t* out_live, uint64_t* out_stale_evictions) {
+  Global& g = G();
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (out_live) *out_live = g.imports.size();
+  if (out_stale_evictions) *out_stale_evictions = g.stale_evictions;
   return TSB_OK;
 }
 
@@ -390,6 +426,7 @@ int tsb_release_all(void) {
     if (e != cudaSuccess) st = cuda_fail(e, "cudaIpcCloseMemHandle");
   }
   g.imports.clear();
+  g.import_by_address.clear();
   return st;
 }
 

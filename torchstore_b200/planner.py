@@ -14,6 +14,7 @@ Two small value types carry everything the native layer needs, with no torch ops
 
 from __future__ import annotations
 
+import weakref
 from dataclasses import dataclass
 from typing import Sequence
 
@@ -153,6 +154,48 @@ def _span_elems(shape, stride) -> int:
     return sum((e - 1) * st for e, st in zip(shape, stride)) + 1
 
 
+class _ExportCache:
+    """Exporter-side registration cache: (data_ptr, nbytes) -> exported region, evicted when the
+    tensor's storage dies -- the counterpart of the reference's RdmaMemoryCache
+    (transport/torchcomms/cache.py:150-186: keyed on (data_ptr, nbytes), weakref on
+    ``untyped_storage()``).  Saves the driver round trips (cuMemGetAddressRange, cudaIpcGetMemHandle)
+    on every get of a stored tensor and on every handle re-publication."""
+
+    def __init__(self) -> None:
+        self._regions: dict[tuple[int, int], tuple[bytes, int]] = {}
+        self._storage_refs: dict[tuple[int, int], weakref.ref] = {}
+        self.hits = self.misses = self.evictions = 0
+
+    def export(self, t: torch.Tensor, nbytes: int) -> tuple[bytes, int]:
+        key = (t.data_ptr(), nbytes)
+        hit = self._regions.get(key)
+        if hit is not None:
+            self.hits += 1
+            return hit
+        self.misses += 1
+        region = _native.export_region(t.data_ptr(), nbytes)
+        entry = (_native.region_to_bytes(region), int(region.device))
+        try:
+            ref = weakref.ref(t.untyped_storage(), lambda _r, _k=key: self._evict(_k))
+        except Exception:  # storage not weak-referenceable: do not cache what cannot be invalidated
+            return entry
+        self._regions[key] = entry
+        self._storage_refs[key] = ref
+        return entry
+
+    def _evict(self, key) -> None:
+        if self._regions.pop(key, None) is not None:
+            self.evictions += 1
+        self._storage_refs.pop(key, None)
+
+    def clear(self) -> None:
+        self._regions.clear()
+        self._storage_refs.clear()
+
+
+export_cache = _ExportCache()
+
+
 @dataclass
 class HbmDescriptor:
     """Where a tensor lives in some GPU's HBM, in a form that survives pickling."""
@@ -170,8 +213,8 @@ class HbmDescriptor:
         if any(st < 0 for st in t.stride()):
             raise ValueError("negative strides are not supported")
         nbytes = _span_elems(t.shape, t.stride()) * t.element_size()
-        region = _native.export_region(t.data_ptr(), max(nbytes, 1))
-        return cls(_native.region_to_bytes(region), tuple(t.shape), tuple(t.stride()), t.dtype, int(region.device))
+        raw, device = export_cache.export(t, max(nbytes, 1))
+        return cls(raw, tuple(t.shape), tuple(t.stride()), t.dtype, device)
 
     @property
     def nbytes(self) -> int:

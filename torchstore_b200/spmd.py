@@ -133,6 +133,7 @@ class _SPMDSession:
             cl = _api._local_clent_map.get(name)
             if cl is not None:
                 state_dict_utils.reset_direct_cache(cl)
+                cl.close_sessions()
                 cl.strategy.transport_context.clear()
             _api.reset_client(name)
             for actor in self._owned:

@@ -52,8 +52,14 @@ class StorageVolume(Actor):
         return await self.store.handshake(transport_buffer, requests)
 
     @endpoint
-    async def put(self, transport_buffer: TransportBuffer, requests: list[Request]) -> None:
+    async def put(self, transport_buffer: TransportBuffer, requests: list[Request]) -> int:
+        """Returns the volume's layout epoch after the put (see InMemoryStore.epoch)."""
         await self.store.put(transport_buffer, requests)
+        return self.store.epoch
+
+    @endpoint
+    async def epoch(self) -> int:
+        return self.store.epoch
 
     @endpoint
     async def get(self, transport_buffer: TransportBuffer, requests: list[Request]) -> TransportBuffer:
@@ -97,6 +103,7 @@ def _pick_device(volume_id: str, device: int | None) -> int | None:
 class StorageImpl:
     def __init__(self) -> None:
         self.transport_context = TransportContext()
+        self.epoch = 0
 
     async def put(self, transport_buffer: TransportBuffer, requests: list[Request]) -> None:
         raise NotImplementedError()
@@ -124,13 +131,17 @@ class InMemoryStore(StorageImpl):
         super().__init__()
         self.kv: dict[str, Any] = {}
         self.device = device
+        # layout epoch: bumped whenever a key starts pointing at OTHER memory (new key, reallocation,
+        # delete, reset) -- never by an in-place overwrite.  A client's cached put/get plan (device
+        # pointers into this volume's arenas) is valid exactly while the epoch it was built under lasts.
+        self.epoch = 0
         self._configure_transport()
 
     def _configure_transport(self) -> None:
         # the HBM transport's volume half allocates stored tensors from this volume's arenas
         from torchstore_b200.transport.hbm import HbmVolumeCache
 
-        self.transport_context.get(HbmVolumeCache).configure(self.device)
+        self.transport_context.get(HbmVolumeCache).configure(self.device, self)
 
     def stats(self) -> dict:
         from torchstore_b200.transport.hbm import HbmVolumeCache
@@ -173,11 +184,18 @@ class InMemoryStore(StorageImpl):
 
     def _store(self, request: Request, data: Any) -> None:
         if request.is_object:
+            if not isinstance(self.kv.get(request.key), dict) or "obj" not in self.kv[request.key]:
+                self.epoch += 1
             self.kv[request.key] = {"obj": data}
         elif request.tensor_slice is not None:
             shards = self.kv.setdefault(request.key, {})
+            old = shards.get(request.tensor_slice.coordinates)
+            if old is None or old.get("tensor") is not data or old.get("slice") != request.tensor_slice:
+                self.epoch += 1
             shards[request.tensor_slice.coordinates] = {"slice": request.tensor_slice, "tensor": data}
         else:
+            if self.kv.get(request.key) is not data:
+                self.epoch += 1
             self.kv[request.key] = data
 
     # -- get ------------------------------------------------------------------------------------
@@ -245,12 +263,15 @@ class InMemoryStore(StorageImpl):
         if key not in self.kv:
             raise KeyError(f"Key '{key}' not found. {list(self.kv.keys())=}")
         del self.kv[key]
+        self.epoch += 1
 
     async def delete_batch(self, keys: list[str]) -> None:
         for key in set(keys):
-            self.kv.pop(key, None)
+            if self.kv.pop(key, None) is not None:
+                self.epoch += 1
 
     def reset(self) -> None:
         self.kv = {}
+        self.epoch += 1
         self.transport_context.clear()
         self._configure_transport()

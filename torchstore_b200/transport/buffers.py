@@ -73,6 +73,7 @@ class TransportBuffer:
 
     def __init__(self, storage_volume_ref: "StorageVolumeRef"):
         self.storage_volume_ref = storage_volume_ref
+        self._volume_epoch = None  # the volume's layout epoch after the last put (storage_volume.py)
 
     # ---- client side ----------------------------------------------------------------------------
     def requires_handshake(self, requests: list[Request]) -> bool:
@@ -91,7 +92,7 @@ class TransportBuffer:
                 await self.perform_handshake(requests, meta, tracker)
             await self._pre_put_hook(requests)
             tracker.track_step("_pre_put_hook")
-            await self.storage_volume_ref.volume.put.call(self, meta)
+            self._volume_epoch = await self.storage_volume_ref.volume.put.call(self, meta)
             tracker.track_step("volume.put.call")
             await self._post_request_success()
             tracker.track_step("_post_request_success")

@@ -20,6 +20,7 @@ GET  1. volume   handle_get_request: descriptor (exported region + layout) of ea
 
 from __future__ import annotations
 
+import collections
 import logging
 import os
 import time
@@ -131,8 +132,13 @@ class HbmVolumeCache(TransportCache):
         self.device: int | None = None
         self._pool: HbmPool | None = None
 
-    def configure(self, device: int | None) -> None:
+    def configure(self, device: int | None, store=None) -> None:
         self.device = device
+        self._store = store
+
+    def epoch_of_store(self) -> int | None:
+        store = getattr(self, "_store", None)
+        return None if store is None else store.epoch
 
     def allocate(self, shape, dtype: torch.dtype) -> torch.Tensor:
         if self.device is None:
@@ -153,19 +159,86 @@ class HbmVolumeCache(TransportCache):
             self._pool = None
 
 
+@dataclass
+class HbmSession:
+    """A replayable put or get of one key batch against one volume: the compiled native plans
+    (device tables with resolved source/destination pointers) and the volume layout epoch they
+    were built under.  While the volume's epoch is unchanged no key of the batch has moved, so the
+    next identical batch is ONE small RPC (the epoch check) + one launch per device."""
+
+    plans: dict  # device -> native plan id
+    epoch: int
+    volume_ref: Any
+
+    async def valid(self) -> bool:
+        return await self.volume_ref.volume.epoch.call_one() == self.epoch
+
+    def launch(self, fence_out: bool = True) -> None:
+        """fence_out=False (puts): the caller's stream may run ahead of the copy -- the source is only
+        read, and completion is observed on the host before the put is reported done."""
+        for dev, plan in self.plans.items():
+            _native.plan_launch(plan, _native.torch_stream(dev), fence_out=fence_out)
+
+    async def wait(self) -> None:
+        from torchstore_b200.direct_weight_sync import wait_plan
+
+        for plan in self.plans.values():
+            await wait_plan(plan)
+
+    def close(self) -> None:
+        for plan in self.plans.values():
+            try:
+                _native.plan_destroy(plan)
+            except Exception as e:
+                logger.warning("plan_destroy failed: %s", e)
+        self.plans = {}
+
+
 class HbmClientCache(TransportCache):
     """Client-side long-lived state.  Region mappings are cached natively per
     (exporter, allocation); clearing the context drops them all
-    (reference SharedMemoryCache.clear, shared_memory.py:246-250)."""
+    (reference SharedMemoryCache.clear, shared_memory.py:246-250).  Also holds the replayable
+    sessions of the store path's fast lane (LRU)."""
+
+    MAX_SESSIONS = int(os.environ.get("TORCHSTORE_B200_MAX_SESSIONS", "64"))
 
     def __init__(self) -> None:
         self.mapped = 0
+        self.put_sessions: "collections.OrderedDict[tuple, HbmSession]" = collections.OrderedDict()
+        self.hits = self.misses = 0
+
+    def lookup(self, sig) -> HbmSession | None:
+        sess = self.put_sessions.get(sig)
+        if sess is not None:
+            self.put_sessions.move_to_end(sig)
+        return sess
+
+    def remember(self, sig, sess: HbmSession) -> None:
+        old = self.put_sessions.pop(sig, None)
+        if old is not None:
+            old.close()
+        self.put_sessions[sig] = sess
+        while len(self.put_sessions) > self.MAX_SESSIONS:
+            _, victim = self.put_sessions.popitem(last=False)
+            victim.close()
+
+    def forget(self, sig) -> None:
+        sess = self.put_sessions.pop(sig, None)
+        if sess is not None:
+            sess.close()
 
     def clear(self) -> None:
+        for sess in self.put_sessions.values():
+            sess.close()
+        self.put_sessions.clear()
         try:
             _native.release_all()
         except Exception as e:
             logger.warning("release_all failed: %s", e)
+
+
+def tensor_sig(t: torch.Tensor) -> tuple:
+    return (t.data_ptr(), tuple(t.shape), tuple(t.stride()), t.dtype)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -199,6 +272,8 @@ class HbmTransportBuffer(TransportBuffer):
     # the reshard kernel writes strided destination rectangles directly, so the client may hand
     # non-contiguous in-place views (the reference restricts to contiguous ones, utils.py:94-96)
     supports_strided_inplace = True
+    # replayable put/get sessions (see HbmSession): LocalClient keys get sessions, this class put sessions
+    supports_fast_lane = True
 
     def __init__(self, storage_volume_ref: "StorageVolumeRef"):
         super().__init__(storage_volume_ref)
@@ -208,6 +283,10 @@ class HbmTransportBuffer(TransportBuffer):
         # identifies THIS put on the volume between handshake and put (two clients may put the same
         # key concurrently; each must get back the landing buffer it wrote into)
         self._nonce = os.urandom(8).hex()
+        self._epoch = None            # volume layout epoch seen by the volume half of a get
+        self._record = False          # client: compile cached plans instead of one-shot copies
+        self._recorded_plans: dict[int, int] = {}
+        self.fast_path_hit = False    # last put was served by a cached session (no handshake, no notify)
 
     def __getstate__(self) -> dict[str, Any]:
         state = self.__dict__.copy()
@@ -223,9 +302,52 @@ class HbmTransportBuffer(TransportBuffer):
         ]
         return True
 
-    async def put_to_storage_volume(self, requests: list[Request]) -> None:
+    def _put_signature(self, requests: list[Request]):
+        """Identity of a put batch for the fast lane: same keys, same source memory, same layout.
+        None when the batch is not replayable (objects, host tensors)."""
+        sig = [self.storage_volume_ref.volume_id]
+        for r in requests:
+            t = r.tensor_val
+            if r.is_object or t is None or not t.is_cuda:
+                return None
+            sig.append((r.key, None if r.tensor_slice is None else r.tensor_slice.coordinates, *tensor_sig(t)))
+        return tuple(sig)
+
+    async def put_to_storage_volume(self, requests: list[Request], wait: bool = True):
+        """Store path fast lane: a batch that was put before (same keys, same source pointers) and
+        whose landing buffers have not moved (volume epoch unchanged) replays its compiled plan --
+        one epoch RPC + one launch per device, no handshake, no per-key work.  With ``wait=False`` the
+        launch is returned un-awaited (an :class:`HbmSession`; ``await sess.wait()`` completes the
+        put), so the copy runs on the side stream while the caller's compute continues."""
         self._needs_handshake = True
-        await super().put_to_storage_volume(requests)
+        self.fast_path_hit = False
+        cache: HbmClientCache = self.storage_volume_ref.transport_context.get(HbmClientCache)
+        sig = self._put_signature(requests) if os.environ.get("TORCHSTORE_B200_FAST_LANE", "1") == "1" else None
+        if sig is not None:
+            sess = cache.lookup(sig)
+            if sess is not None:
+                if await sess.valid():
+                    cache.hits += 1
+                    sess.launch(fence_out=False)
+                    self.fast_path_hit = True
+                    if not wait:
+                        return sess
+                    await sess.wait()
+                    return None
+                cache.forget(sig)
+            cache.misses += 1
+            self._record = True
+        try:
+            await super().put_to_storage_volume(requests)
+            if self._record and self._recorded_plans and self._volume_epoch is not None:
+                cache.remember(sig, HbmSession(self._recorded_plans, int(self._volume_epoch), self.storage_volume_ref))
+                self._recorded_plans = {}
+        finally:
+            for plan in self._recorded_plans.values():  # failed before the session was stored
+                _native.plan_destroy(plan)
+            self._recorded_plans = {}
+            self._record = False
+        return None
 
     async def recv_handshake(self, ctx: "TransportContext", entries: list[tuple[Request, Any]]) -> list[Any]:
         """Volume: hand out where each tensor must be written."""
@@ -273,10 +395,16 @@ class HbmTransportBuffer(TransportBuffer):
         from torchstore_b200.direct_weight_sync import _fence_in
 
         devices = set()
+        record = self._record and not host_copies
         for dev, pairs in per_device.items():
             rects, n = build_rects(pairs)
-            _fence_in(dev)
-            _native.copy_rects(dev, rects, n)
+            if record:
+                # fast lane: keep the compiled tables; the next identical batch replays them
+                plan = self._recorded_plans[dev] = _native.plan_create(dev, rects, n)
+                _native.plan_launch(plan, _native.torch_stream(dev), fence_out=False)
+            else:
+                _fence_in(dev)
+                _native.copy_rects(dev, rects, n)
             devices.add(dev)
         for src, desc in host_copies:
             dev = desc.device if _same_process(desc) else torch.cuda.current_device()
@@ -303,6 +431,7 @@ class HbmTransportBuffer(TransportBuffer):
     # ---- GET ------------------------------------------------------------------------------------
     async def handle_get_request(self, ctx: "TransportContext", entries: list[tuple[Request, Any]]) -> None:
         self._contexts = []
+        self._epoch = ctx.get(HbmVolumeCache).epoch_of_store()
         for request, data in entries:
             if request.is_object or not isinstance(data, torch.Tensor):
                 self._contexts.append(HbmContext(objects=data, use_rpc=True))
@@ -349,11 +478,19 @@ class HbmTransportBuffer(TransportBuffer):
         from torchstore_b200.direct_weight_sync import _fence_in
 
         devices = set()
+        record = self._record and not d2h
+        self._epoch = transport_buffer._epoch
         for dev, pairs in per_device.items():
             rects, n = build_rects(pairs)
-            _fence_in(dev)
-            _native.copy_rects(dev, rects, n)
+            if record:
+                plan = self._recorded_plans[dev] = _native.plan_create(dev, rects, n)
+                _native.plan_launch(plan, _native.torch_stream(dev))
+            else:
+                _fence_in(dev)
+                _native.copy_rects(dev, rects, n)
             devices.add(dev)
+        if not record:
+            self._record = False  # something in this batch is not replayable (host / object results)
         staged = []
         for i, desc, dest in d2h:
             dev = desc.device if _same_process(desc) else torch.cuda.current_device()
@@ -386,6 +523,17 @@ class HbmTransportBuffer(TransportBuffer):
             else:
                 results[i] = host
         return results
+
+    def take_session(self) -> HbmSession | None:
+        """Client, after a recorded get: the replayable session of this volume's part (or None)."""
+        if not self._record or not self._recorded_plans or self._epoch is None:
+            for plan in self._recorded_plans.values():
+                _native.plan_destroy(plan)
+            self._recorded_plans = {}
+            return None
+        sess = HbmSession(self._recorded_plans, int(self._epoch), self.storage_volume_ref)
+        self._recorded_plans = {}
+        return sess
 
     async def drop(self) -> None:
         self._contexts = []
