@@ -251,6 +251,23 @@ int tsb_host_unregister(void* ptr);
 enum { TSB_H2D = 1, TSB_D2H = 2, TSB_D2D = 3 };
 int tsb_memcpy_async(int device, void* dst, const void* src, uint64_t nbytes, int kind, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* host tier: POSIX shm segments + strided host mover, for CPU tensors and GPU-less volumes     */
+/*   reference: allocate_shared_tensor / SharedMemoryCache   transport/shared_memory.py:40-46,210-260 */
+/*              shm_tensor.copy_(t) / client_tensor.copy_(shm) transport/shared_memory.py:373-374,473-476 */
+/*   These calls need no CUDA device.  GPU tensors never use them (no fallback: the tier is chosen */
+/*   by tensor device / transport type).                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Create (exclusive) / attach / detach / unlink a named segment ("/name").  create prefaults. */
+int tsb_shm_create(const char* name, uint64_t nbytes, void** out_ptr);
+int tsb_shm_attach(const char* name, uint64_t nbytes, void** out_ptr);
+int tsb_shm_detach(void* ptr, uint64_t nbytes);
+int tsb_shm_unlink(const char* name);
+/* Same descriptors as tsb_copy_rects with HOST pointers and src_dtype == dst_dtype: strided byte
+ * moves on `threads` host threads (byte-balanced split of the flattened row space). */
+int tsb_host_copy_rects(const tsb_rect_t* rects, uint64_t n, uint32_t threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,28 @@ def _worker(rank, world, port, pg_port, outdir):
         res["sd"] = await ts.get_state_dict("sd")
         res["exists_missing"] = await ts.exists("nope")
         dist.barrier()
+        # host tier across processes (no GPU here): every rank owns rows [rank*R, (rank+1)*R) of a
+        # [world*R, C] fp32 weight (FSDP Shard(0)) in ITS volume's POSIX shm segments; each rank then
+        # reads its TP Shard(1) columns in place from all volumes, and the whole tensor
+        import torch
+
+        from torchstore_b200.transport import create_transport_buffer
+        from torchstore_b200.transport.types import Request, TensorSlice
+
+        R, C = 64, 96
+        full = torch.arange(world * R * C, dtype=torch.float32).reshape(world * R, C)
+        req = Request.from_any("w", full[rank * R:(rank + 1) * R].contiguous(),
+                               TensorSlice((rank * R, 0), (rank,), (world * R, C), (R, C), (world,)))
+        ref = c.strategy.select_storage_volume()
+        await create_transport_buffer(ref).put_to_storage_volume([req])
+        await c._controller.notify_put_batch.call([req.meta_only()], ref.volume_id)
+        dist.barrier()
+        cw = C // world
+        dest = torch.zeros(world * R, cw)
+        got = await ts.get("w", dest, TensorSlice((0, rank * cw), (rank,), (world * R, C), (world * R, cw), (world,)))
+        res["reshard_ok"] = bool(got is dest and torch.equal(dest, full[:, rank * cw:(rank + 1) * cw]))
+        res["full_ok"] = bool(torch.equal(await ts.get("w"), full))
+        dist.barrier()
         await ts.shutdown()
         # the same job can bring the store up again: nothing of the first incarnation leaks in
         await ts.initialize_spmd(ts.LocalRankStrategy())
@@ -92,6 +114,7 @@ def test_two_rank_spmd_store_on_cpu():
         assert out[r]["my_volume"] == [str(r)]
         assert out[r]["sd"] == {"step": 11, "cfg": {"a": 1}}
         assert out[r]["exists_missing"] is False
+        assert out[r]["reshard_ok"] and out[r]["full_ok"]
         assert out[r]["second_keys"] == [] and out[r]["second_peer"] == other
 
 

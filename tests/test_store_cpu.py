@@ -1,6 +1,7 @@
 """Control-plane behaviour on a GPU-less box: objects travel by value through the same
 client -> transport -> volume -> controller path as tensors (reference tests/test_store.py,
-tests/test_keys.py), and tensor puts fail loudly because there is no host data plane."""
+tests/test_keys.py); the HBM tier refuses to work without a GPU (tensor data on a GPU-less box goes
+through the host tier, tests/test_host_tier.py)."""
 
 import asyncio
 import os
@@ -117,11 +118,12 @@ def test_state_dict_of_objects_and_missing_mapping():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a GPU-less box")
-def test_tensor_put_without_gpu_fails_loudly():
+def test_hbm_tier_without_gpu_fails_loudly():
+    """Asking for the NVLink/HBM transport on a box without a GPU must fail, not degrade."""
     async def main():
-        await ts.initialize()
+        await ts.initialize(num_storage_volumes=1, strategy=ts.ControllerStorageVolumes(ts.TransportType.NVLink))
         try:
-            with pytest.raises(Exception, match="no host-memory fallback|no CUDA|CUDA"):
+            with pytest.raises(Exception, match="no GPU|no CUDA|CUDA"):
                 await ts.put("t", torch.zeros(4))
         finally:
             await ts.shutdown()
@@ -129,9 +131,10 @@ def test_tensor_put_without_gpu_fails_loudly():
     run(main())
 
 
-def test_other_transports_are_rejected():
+@pytest.mark.parametrize("kind", ["Gloo", "MonarchRPC", "MonarchRDMA", "TorchComms"])
+def test_other_transports_are_rejected(kind):
     async def main():
-        await ts.initialize(num_storage_volumes=1, strategy=ts.ControllerStorageVolumes(ts.TransportType.SharedMemory))
+        await ts.initialize(num_storage_volumes=1, strategy=ts.ControllerStorageVolumes(getattr(ts.TransportType, kind)))
         try:
             with pytest.raises(RuntimeError, match="not part of the B200 build"):
                 await ts.put("x", 1)

@@ -12,7 +12,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtstore_b200.so")
-SOURCES = ["copy_rects.cu", "plan.cu", "runtime.cu"]
+SOURCES = ["copy_rects.cu", "plan.cu", "runtime.cu", "host_tier.cu"]
 HEADERS = [os.path.join(CSRC, "tsb_internal.h"), os.path.join(REPO_ROOT, "include", "tstore_b200.h")]
 
 NVCC_FLAGS = [

@@ -147,6 +147,11 @@ _SIGNATURES = {
     "tsb_host_register": (C.c_int, [_vp, C.c_uint64]),
     "tsb_host_unregister": (C.c_int, [_vp]),
     "tsb_memcpy_async": (C.c_int, [C.c_int, _vp, _vp, C.c_uint64, C.c_int, _vp]),
+    "tsb_shm_create": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(_vp)]),
+    "tsb_shm_attach": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(_vp)]),
+    "tsb_shm_detach": (C.c_int, [_vp, C.c_uint64]),
+    "tsb_shm_unlink": (C.c_int, [C.c_char_p]),
+    "tsb_host_copy_rects": (C.c_int, [C.POINTER(Rect), C.c_uint64, C.c_uint32]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -468,3 +473,28 @@ def host_unregister(ptr: int) -> None:
 def memcpy_async(device: int, dst: int, src: int, nbytes: int, kind: int, stream: int | None = None) -> None:
     check(lib().tsb_memcpy_async(device, C.c_void_p(dst), C.c_void_p(src), nbytes, kind,
                                  C.c_void_p(stream) if stream else None))
+
+
+# ---- host tier (no CUDA device needed) -----------------------------------------------------------
+def shm_create(name: str, nbytes: int) -> int:
+    out = C.c_void_p()
+    check(lib().tsb_shm_create(name.encode(), nbytes, C.byref(out)))
+    return int(out.value)
+
+
+def shm_attach(name: str, nbytes: int) -> int:
+    out = C.c_void_p()
+    check(lib().tsb_shm_attach(name.encode(), nbytes, C.byref(out)))
+    return int(out.value)
+
+
+def shm_detach(ptr: int, nbytes: int) -> None:
+    check(lib().tsb_shm_detach(C.c_void_p(ptr), nbytes))
+
+
+def shm_unlink(name: str) -> None:
+    check(lib().tsb_shm_unlink(name.encode()))
+
+
+def host_copy_rects(rects, n: int, threads: int = 1) -> None:
+    check(lib().tsb_host_copy_rects(rects, n, threads))

@@ -365,7 +365,7 @@ class LocalClient:
         from torchstore_b200 import _native
         from torchstore_b200.transport.hbm import _wait, get_result_device
 
-        if get_result_device() == "cuda":
+        if get_result_device() == "cuda" or not gathered.is_cuda:
             return gathered
         host = torch.empty(gathered.shape, dtype=gathered.dtype)
         dev = gathered.device.index
