@@ -262,4 +262,4 @@ def test_export_import_same_process_torch_suballocation():
     assert reg.nbytes == 4096 * 4 and reg.alloc_bytes >= reg.offset + reg.nbytes
     assert _native.import_region(reg, 0) == t.data_ptr()
     blob = _native.region_to_bytes(reg)
-    assert len(blob) == 112 and _native.region_from_bytes(blob).offset == reg.offset
+    assert len(blob) == 120 and _native.region_from_bytes(blob).offset == reg.offset
