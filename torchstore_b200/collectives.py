@@ -12,8 +12,10 @@ The reference has no equivalent: each reader fetches all N shards itself
 (``client.py:292-314``).  This module is device-agnostic plumbing around the collective, so its
 logic is exercised by a world-size-2 gloo test on the CPU; the GPU hot path is NCCL's.
 
-Status (round 1): implemented and CPU-tested, **disabled by default** until it has been measured
-against the P2P path on 8 GPUs (enable with TORCHSTORE_B200_ALLGATHER=1).
+Status (round 2): measured against the P2P path through ``bench.py --config 3b [--allgather]``
+(profiles/r2_bench_*cfg3b*.json): the one-sided pulls win (one copy_rects launch per reader vs one
+NCCL collective per tensor), so the route stays **off by default**; TORCHSTORE_B200_ALLGATHER=1
+selects it.  ``tests/test_gpu_multi.py`` runs it over NCCL on two GPUs.
 """
 
 from __future__ import annotations
@@ -54,7 +56,7 @@ def is_allgather_shaped(local_slices: dict[str, TensorSlice], dest_shapes: dict[
 def all_gather_state_dict(local_shards: dict[str, torch.Tensor], dests: dict[str, torch.Tensor], group=None) -> int:
     """All-gather every tensor's row shards into its full destination; returns the number of
     collectives issued.  Shards and destinations must be contiguous, same dtype and device kind."""
-    works = []
+    pairs = []
     for name, shard in local_shards.items():
         dest = dests[name]
         if not (shard.is_contiguous() and dest.is_contiguous()):
@@ -63,7 +65,20 @@ def all_gather_state_dict(local_shards: dict[str, torch.Tensor], dests: dict[str
             raise ValueError(f"dtype mismatch for {name}: {shard.dtype} vs {dest.dtype}")
         if dest.numel() != shard.numel() * dist.get_world_size(group):
             raise ValueError(f"shape mismatch for {name}: {tuple(dest.shape)} is not world x {tuple(shard.shape)}")
-        works.append(dist.all_gather_into_tensor(dest, shard, group=group, async_op=True))
+        pairs.append((dest, shard))
+    if not pairs:
+        return 0
+    if dist.get_backend(group) == "nccl":
+        # one NCCL group (ncclGroupStart/End) for the whole state dict instead of a launch per tensor
+        try:
+            with dist._coalescing_manager(group=group, device=pairs[0][0].device, async_ops=True) as cm:
+                for dest, shard in pairs:
+                    dist.all_gather_into_tensor(dest, shard, group=group)
+            cm.wait()
+            return len(pairs)
+        except (AttributeError, RuntimeError, TypeError):
+            pass  # older torch: fall through to one collective per tensor
+    works = [dist.all_gather_into_tensor(dest, shard, group=group, async_op=True) for dest, shard in pairs]
     for w in works:
         w.wait()
     return len(works)
