@@ -88,6 +88,8 @@ def test_llama3_8b_plans_match_reference_statistics_and_cover_exactly(n):
         assert len(dr) == len(pairs)  # rects map 1:1 to pairs here (no splitting at these sizes)
         assert np.array_equal(is_link, src_dev != dest_rank)
         assert info.link_bytes == info.remote_src_bytes
+        if n > 1:  # ring depth follows the fan-in: 6 stages from 4 source GPUs up, 3 below
+            assert info.link_stages == (6 if n - 1 >= 4 else 3)
         tile_units = np.where(is_link, info.link_tile_bytes // 16, info.tile_bytes // 16)
         assert np.array_equal(dr["tile_units"], tile_units)
         assert len(tiles) == info.num_tiles + info.num_link_tiles

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -121,6 +122,7 @@ struct Tuning {
   // lengthen the queues at the source GPU, whose HBM is busy with its own copy (profiles/r2_sweep_x2_*)
   uint32_t link_tile_units = 256;
   uint32_t link_stages = 3;
+  bool link_stages_auto = true;     // no TSB_LINK_STAGES: pick the depth from the number of source GPUs
   bool link = true;
   bool link_all = false;  // TSB_LINK=2: local sources too (exercises the link warp on one GPU)
 };
@@ -140,6 +142,7 @@ Tuning default_tuning() {
   sb = std::min<uint32_t>(16384u, std::max<uint32_t>(1024u, sb)) / 16 * 16;
   t.link_tile_units = sb / 16;
   t.link_stages = std::min<uint32_t>(8u, std::max<uint32_t>(3u, env_u32("TSB_LINK_STAGES", 3)));
+  t.link_stages_auto = getenv("TSB_LINK_STAGES") == nullptr;
   const uint32_t lk = env_u32("TSB_LINK", 1);
   t.link = lk != 0;
   t.link_all = lk == 2;
@@ -392,6 +395,15 @@ int compile(int device, const tsb_rect_t* rects, uint64_t n, uint32_t flags, con
   uint64_t total = 0;
   for (uint32_t t : c.rect_tiles) total += t;
   if (total >= (1ull << 32)) return fail(TSB_ERR_UNSUPPORTED, "plan has more than 2^32 tiles");
+  if (c.tune.link_stages_auto) {
+    // Ring depth by fan-in, measured on the real jobs (profiles/r2_bench_8gpu_sweep_n{4,8}.json): with 7 source
+    // GPUs each NVSwitch path carries 1/7 of the stream and 6 stages win (0.815 vs 0.851 ms at N=8); with
+    // <= 3 sources the deeper ring only lengthens the queues at the busy sources (1.56 vs 1.48 ms at N=4).
+    std::set<int32_t> sources;
+    for (size_t i = 0; i < c.rects.size(); ++i)
+      if (c.rects[i].link) sources.insert(c.rect_src_device[i]);
+    c.tune.link_stages = sources.size() >= 4 ? 6u : 3u;
+  }
   c.order(false, flags, 1, &out->tiles);
   c.order(true, flags, kLinkBatch, &out->link_tiles);
   c.info.num_rects = c.rects.size();
