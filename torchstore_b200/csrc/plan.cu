@@ -411,7 +411,7 @@ int compile(int device, const tsb_rect_t* rects, uint64_t n, uint32_t flags, con
   c.info.num_link_tiles = out->link_tiles.size();
   c.info.tile_bytes = tune.tile_units * 16;
   c.info.link_tile_bytes = tune.link_tile_units * 16;
-  c.info.link_stages = tune.link_stages;
+  c.info.link_stages = c.tune.link_stages;
   c.info.block = kCopyThreads + (out->link_tiles.empty() ? 0u : kLinkThreads);
   return TSB_OK;
 }
