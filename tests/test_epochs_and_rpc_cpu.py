@@ -181,3 +181,38 @@ def test_double_initialize_is_refused_before_touching_the_live_store():
             await ts.shutdown()
 
     run(main())
+
+
+def test_epoch_board_mirrors_controller_and_volume_epochs_in_shared_memory():
+    import glob
+    import os
+
+    from torchstore_b200 import epoch_board
+
+    async def main():
+        await ts.initialize(num_storage_volumes=2, strategy=ts.LocalRankStrategy(ts.TransportType.SharedMemory))
+        try:
+            cl = await ts.client()
+            name, slots = cl.strategy.epoch_board
+            assert sorted(slots) == ["0", "1"] and sorted(slots.values()) == [1, 2]
+            assert os.path.exists("/dev/shm" + name)
+            board = epoch_board.attached(name)
+            vol0 = rpc._lookup("torchstore/volume/0")[0]
+            ctrl = rpc._lookup("torchstore/controller")[0]
+            assert board.read(0) == ctrl.epoch and board.read(slots["0"]) == vol0.store.epoch
+            await ts.put("a", torch.zeros(8))
+            assert board.read(0) == ctrl.epoch > 0 and board.read(slots["0"]) == vol0.store.epoch > 0
+            before = (board.read(0), board.read(slots["0"]))
+            await ts.put("a", torch.ones(8))                       # in place: neither epoch moves
+            assert (board.read(0), board.read(slots["0"])) == before
+            await ts.delete("a")
+            assert board.read(0) > before[0] and board.read(slots["0"]) > before[1]
+            assert board.read(slots["1"]) == rpc._lookup("torchstore/volume/1")[0].store.epoch
+            # a StorageVolumeRef carries the board so transports can find their slot
+            assert cl.strategy.get_storage_volume("1").epoch_board == (name, slots)
+            return name
+        finally:
+            await ts.shutdown()
+
+    name = run(main())
+    assert not os.path.exists("/dev/shm" + name) and not glob.glob("/dev/shm/tsb200_epochs_*")

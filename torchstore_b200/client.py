@@ -192,8 +192,11 @@ class LocalClient:
         sess = self._get_sessions.get(sig)
         if sess is None:
             return None
-        checks = [self._controller.get_epoch.call_one()] + [p.valid() for p in sess.parts]
-        got = await asyncio.gather(*checks)
+        board = self._epoch_board()
+        if board is not None:
+            got = [board.read(0)] + [await p.valid() for p in sess.parts]  # memory loads, no RPC
+        else:
+            got = await asyncio.gather(self._controller.get_epoch.call_one(), *[p.valid() for p in sess.parts])
         if got[0] != sess.controller_epoch or not all(got[1:]):
             self._drop_get_session(sig)
             return None
@@ -204,6 +207,14 @@ class LocalClient:
             await p.wait()
         self.get_session_hits += 1
         return dict(sess.final)
+
+    def _epoch_board(self):
+        info = getattr(self.strategy, "epoch_board", None)
+        if not info:
+            return None
+        from torchstore_b200 import epoch_board
+
+        return epoch_board.attached(info[0])
 
     def _drop_get_session(self, sig) -> None:
         sess = self._get_sessions.pop(sig, None)
@@ -234,6 +245,11 @@ class LocalClient:
     def close_sessions(self) -> None:
         for sig in list(self._get_sessions):
             self._drop_get_session(sig)
+        info = getattr(self.strategy, "epoch_board", None)
+        if info:
+            from torchstore_b200 import epoch_board
+
+            epoch_board.forget(info[0])
 
     def _apply_inplace(self, fetched: Any, inplace_tensor, request: Request) -> Any:
         """Always hand back the caller's object; copy only if the fetch could not land in place."""
@@ -248,7 +264,8 @@ class LocalClient:
             # read BEFORE the volume map: if the index changes in between, the session is born stale
             # (and is dropped on its first replay) rather than wrongly valid
             try:
-                epoch = await self._controller.get_epoch.call_one()
+                board = self._epoch_board()
+                epoch = board.read(0) if board is not None else await self._controller.get_epoch.call_one()
             except Exception:
                 record_sig = None
         volume_maps = await self._locate_volumes([r.key for r in requests])

@@ -61,6 +61,12 @@ class Controller(Actor):
         # bumped whenever the index changes SHAPE (new key / volume / slice, any delete); overwriting
         # an indexed key in place leaves it alone.  Clients validate cached get plans against it.
         self.epoch = 0
+        self._board = None  # EpochBoard owned by this controller (slot 0 = self.epoch)
+
+    def _bump(self) -> None:
+        self.epoch += 1
+        if self._board is not None:
+            self._board.write(0, self.epoch)
 
     def assert_initialized(self) -> None:
         assert self.is_initialized, "Please call torchstore.initialize before attempting to use store."
@@ -90,7 +96,37 @@ class Controller(Actor):
         self.storage_volumes = storage_volumes
         self.num_storage_volumes = num_storage_volumes
         await self.strategy.set_storage_volumes(self.storage_volumes)
+        await self._publish_epoch_board()
         self.is_initialized = True
+
+    async def _publish_epoch_board(self) -> None:
+        """One shm page with this controller's epoch and every volume's (epoch_board.py): clients on
+        the box validate replayable sessions without an RPC.  Best effort."""
+        from torchstore_b200.epoch_board import MAX_SLOTS, EpochBoard
+
+        volume_ids = sorted(self.strategy.volume_id_to_coord)
+        if len(volume_ids) + 1 > MAX_SLOTS:
+            return
+        board = EpochBoard.create()
+        if board is None:
+            return
+        board.write(0, self.epoch)
+        slots = {vid: i + 1 for i, vid in enumerate(volume_ids)}
+        try:
+            for vid, slot in slots.items():
+                ref = self.storage_volumes.slice(**self.strategy.volume_id_to_coord[vid]) if hasattr(self.storage_volumes, "slice") \
+                    else self.storage_volumes
+                ok = await ref.attach_epoch_board.call_one(board.name, slot)
+                if not ok:
+                    raise RuntimeError(f"volume {vid} could not attach")
+        except Exception as e:  # a volume on another host, an old volume ...: stay on RPC epochs
+            import logging
+
+            logging.getLogger(__name__).debug("epoch board disabled: %s", e)
+            board.close()
+            return
+        self._board = board
+        self.strategy.epoch_board = (board.name, slots)
 
     @endpoint
     async def get_controller_strategy(self) -> TorchStoreStrategy:
@@ -132,11 +168,11 @@ class Controller(Actor):
         if storage_volume_id in volume_map:
             known = volume_map[storage_volume_id]
             if request.tensor_slice not in known.tensor_slices:
-                self.epoch += 1
+                self._bump()
             known.update(info)
         else:
             volume_map[storage_volume_id] = info
-            self.epoch += 1
+            self._bump()
 
     @endpoint
     async def get_epoch(self) -> int:
@@ -146,10 +182,16 @@ class Controller(Actor):
     async def teardown(self) -> None:
         self.is_initialized = False
         self.keys_to_storage_volumes = KeyIndex()
-        self.epoch += 1
+        self._bump()
         self.strategy = None
         if self.storage_volumes is not None:
             await self.storage_volumes.reset.call()
+        if self._board is not None:
+            from torchstore_b200 import epoch_board
+
+            epoch_board.forget(self._board.name)  # this process's reader attachment (client + local volumes)
+            self._board.close()                    # the owner's mapping; unlinks the segment
+            self._board = None
         self.storage_volumes = None
         self.num_storage_volumes = None
 
@@ -175,7 +217,7 @@ class Controller(Actor):
                 return
             raise KeyError(f"Unable to locate {key} in storage volume {storage_volume_id}.")
         del volume_map[storage_volume_id]
-        self.epoch += 1
+        self._bump()
         if not volume_map:
             del self.keys_to_storage_volumes[key]
 

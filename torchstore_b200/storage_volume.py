@@ -62,6 +62,11 @@ class StorageVolume(Actor):
         return self.store.epoch
 
     @endpoint
+    async def attach_epoch_board(self, name: str, slot: int) -> bool:
+        """Mirror this volume's layout epoch into slot `slot` of the controller's epoch board."""
+        return self.store.attach_epoch_board(name, slot)
+
+    @endpoint
     async def get(self, transport_buffer: TransportBuffer, requests: list[Request]) -> TransportBuffer:
         return await self.store.get(transport_buffer, requests)
 
@@ -104,6 +109,30 @@ class StorageImpl:
     def __init__(self) -> None:
         self.transport_context = TransportContext()
         self.epoch = 0
+        self._board = None
+        self._board_slot = 0
+
+    def _bump(self) -> None:
+        self.epoch += 1
+        if self._board is not None:
+            self._board.write(self._board_slot, self.epoch)
+
+    def attach_epoch_board(self, name: str, slot: int) -> bool:
+        from torchstore_b200 import epoch_board
+
+        board = epoch_board.attached(name)
+        if board is None:
+            return False
+        self._board, self._board_slot, self._board_name = board, slot, name
+        board.write(slot, self.epoch)
+        return True
+
+    def detach_epoch_board(self) -> None:
+        if self._board is not None:
+            from torchstore_b200 import epoch_board
+
+            self._board = None
+            epoch_board.forget(getattr(self, "_board_name", None))
 
     async def put(self, transport_buffer: TransportBuffer, requests: list[Request]) -> None:
         raise NotImplementedError()
@@ -134,7 +163,6 @@ class InMemoryStore(StorageImpl):
         # layout epoch: bumped whenever a key starts pointing at OTHER memory (new key, reallocation,
         # delete, reset) -- never by an in-place overwrite.  A client's cached put/get plan (device
         # pointers into this volume's arenas) is valid exactly while the epoch it was built under lasts.
-        self.epoch = 0
         self._configure_transport()
 
     def _configure_transport(self) -> None:
@@ -185,17 +213,17 @@ class InMemoryStore(StorageImpl):
     def _store(self, request: Request, data: Any) -> None:
         if request.is_object:
             if not isinstance(self.kv.get(request.key), dict) or "obj" not in self.kv[request.key]:
-                self.epoch += 1
+                self._bump()
             self.kv[request.key] = {"obj": data}
         elif request.tensor_slice is not None:
             shards = self.kv.setdefault(request.key, {})
             old = shards.get(request.tensor_slice.coordinates)
             if old is None or old.get("tensor") is not data or old.get("slice") != request.tensor_slice:
-                self.epoch += 1
+                self._bump()
             shards[request.tensor_slice.coordinates] = {"slice": request.tensor_slice, "tensor": data}
         else:
             if self.kv.get(request.key) is not data:
-                self.epoch += 1
+                self._bump()
             self.kv[request.key] = data
 
     # -- get ------------------------------------------------------------------------------------
@@ -263,15 +291,16 @@ class InMemoryStore(StorageImpl):
         if key not in self.kv:
             raise KeyError(f"Key '{key}' not found. {list(self.kv.keys())=}")
         del self.kv[key]
-        self.epoch += 1
+        self._bump()
 
     async def delete_batch(self, keys: list[str]) -> None:
         for key in set(keys):
             if self.kv.pop(key, None) is not None:
-                self.epoch += 1
+                self._bump()
 
     def reset(self) -> None:
         self.kv = {}
-        self.epoch += 1
+        self._bump()
+        self._board = None  # the controller that published the board is tearing the store down
         self.transport_context.clear()
         self._configure_transport()

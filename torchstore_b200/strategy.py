@@ -31,15 +31,16 @@ def current_spawn_rank() -> int:
 
 
 class StorageVolumeRef:
-    __slots__ = ("volume", "volume_id", "transport_context", "default_transport_type", "volume_hostname")
+    __slots__ = ("volume", "volume_id", "transport_context", "default_transport_type", "volume_hostname", "epoch_board")
 
     def __init__(self, volume: "StorageVolume", volume_id: str, transport_context: TransportContext,
-                 default_transport_type: TransportType, volume_hostname: str | None = None):
+                 default_transport_type: TransportType, volume_hostname: str | None = None, epoch_board=None):
         self.volume = volume
         self.volume_id = volume_id
         self.transport_context = transport_context  # survives across requests: caches live here
         self.default_transport_type = default_transport_type
         self.volume_hostname = volume_hostname
+        self.epoch_board = epoch_board  # (shm name, {volume_id: slot}) or None
 
 
 class TorchStoreStrategy:
@@ -52,6 +53,7 @@ class TorchStoreStrategy:
         self.volume_id_to_coord: dict = {}
         self.volume_id_to_hostname: dict = {}
         self.transport_context = TransportContext()
+        self.epoch_board = None  # (shm name, {volume_id: slot}) published by the controller, or None
 
     def __str__(self) -> str:
         n = len(self.storage_volumes) if self.storage_volumes is not None else 0
@@ -97,6 +99,7 @@ class TorchStoreStrategy:
             self.transport_context,
             self.default_transport_type,
             volume_hostname=self.volume_id_to_hostname.get(volume_id),
+            epoch_board=getattr(self, "epoch_board", None),
         )
 
 

@@ -169,8 +169,11 @@ class HbmSession:
     plans: dict  # device -> native plan id
     epoch: int
     volume_ref: Any
+    board: Any = None   # (EpochBoard, slot): read the volume's epoch from shared memory instead of by RPC
 
     async def valid(self) -> bool:
+        if self.board is not None:
+            return self.board[0].read(self.board[1]) == self.epoch
         return await self.volume_ref.volume.epoch.call_one() == self.epoch
 
     def launch(self, fence_out: bool = True) -> None:
@@ -235,6 +238,19 @@ class HbmClientCache(TransportCache):
             _native.release_all()
         except Exception as e:
             logger.warning("release_all failed: %s", e)
+
+
+def _board_slot(volume_ref):
+    """(EpochBoard, slot) of a volume when the controller published an epoch board, else None."""
+    info = getattr(volume_ref, "epoch_board", None)
+    if not info:
+        return None
+    from torchstore_b200 import epoch_board
+
+    name, slots = info
+    board = epoch_board.attached(name)
+    slot = slots.get(volume_ref.volume_id)
+    return (board, slot) if board is not None and slot is not None else None
 
 
 def tensor_sig(t: torch.Tensor) -> tuple:
@@ -340,7 +356,8 @@ class HbmTransportBuffer(TransportBuffer):
         try:
             await super().put_to_storage_volume(requests)
             if self._record and self._recorded_plans and self._volume_epoch is not None:
-                cache.remember(sig, HbmSession(self._recorded_plans, int(self._volume_epoch), self.storage_volume_ref))
+                cache.remember(sig, HbmSession(self._recorded_plans, int(self._volume_epoch), self.storage_volume_ref,
+                                               _board_slot(self.storage_volume_ref)))
                 self._recorded_plans = {}
         finally:
             for plan in self._recorded_plans.values():  # failed before the session was stored
@@ -531,7 +548,7 @@ class HbmTransportBuffer(TransportBuffer):
                 _native.plan_destroy(plan)
             self._recorded_plans = {}
             return None
-        sess = HbmSession(self._recorded_plans, int(self._epoch), self.storage_volume_ref)
+        sess = HbmSession(self._recorded_plans, int(self._epoch), self.storage_volume_ref, _board_slot(self.storage_volume_ref))
         self._recorded_plans = {}
         return sess
 
