@@ -174,6 +174,16 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
 
     ``transport`` / ``monarch_port`` are accepted for signature compatibility (the control plane is
     localhost sockets on one box).  ``rendezvous`` may pass an existing c10d store."""
+    import time
+
+    t_begin = time.perf_counter()
+
+    def trace(what: str) -> None:
+        if os.environ.get("TSB_TRACE_INIT"):
+            import sys
+
+            print(f"[spmd r{os.environ.get('RANK', '?')} +{time.perf_counter() - t_begin:6.2f}s] {what}", file=sys.stderr, flush=True)
+
     strategy = _validate_strategy(strategy)
     if store_name in _api._spmd_state_map:
         raise RuntimeError(f"TorchStore '{store_name}' is already initialized")
@@ -186,7 +196,9 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
     # k-th initialisation of this store name in this job: every rank bumps its own counter, so all
     # ranks derive the same generation and never read keys of an earlier incarnation
     gen = int(rendezvous.add(_spmd_key(store_name, f"generation/{env.rank}"), 1))
+    trace("rendezvous open")
     rpc.ActorServer.instance()  # start this process' actor server (idempotent)
+    trace("actor server up")
     owned: list[str] = []
     hosts_volume = isinstance(strategy, LocalRankStrategy) or env.local_rank == 0
     if hosts_volume:
@@ -198,6 +210,7 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
         owned.append(vol_name)
         vol_ref = rpc.register_actor(vol_name, vol)
         rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}", gen), pickle.dumps(vol_ref))
+        trace("volume registered")
     else:
         rendezvous.set(_spmd_key(store_name, f"volume/{env.rank}", gen), pickle.dumps(None))
 
@@ -210,12 +223,15 @@ async def initialize(strategy: TorchStoreStrategy | None = None, store_name: str
                 members.append(({"gpus": r}, ref))
         name = f"{store_name}/g{gen}/controller"
         owned.append(name)
+        trace("all volume refs collected")
         controller = rpc.register_actor(name, Controller())
         await controller.init.call(strategy=strategy, num_storage_volumes=len(members),
                                    storage_volumes=rpc.ActorMesh(members))
+        trace("controller initialised")
         rendezvous.set(controller_key, pickle.dumps(controller))
     else:
         controller = pickle.loads(rendezvous.get(controller_key))
+        trace("controller ref received")
     _api._spmd_state_map[store_name] = _SPMDSession(rendezvous=rendezvous, controller=controller, store_name=store_name,
                                                    is_primary=(env.rank == 0), env=env, owned_actors=owned, generation=gen)
 
