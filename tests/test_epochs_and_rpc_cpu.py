@@ -216,3 +216,15 @@ def test_epoch_board_mirrors_controller_and_volume_epochs_in_shared_memory():
 
     name = run(main())
     assert not os.path.exists("/dev/shm" + name) and not glob.glob("/dev/shm/tsb200_epochs_*")
+
+
+def test_epoch_board_also_serves_the_default_single_volume_store():
+    async def main():
+        await ts.initialize(num_storage_volumes=1, strategy=ts.ControllerStorageVolumes(ts.TransportType.SharedMemory))
+        try:
+            cl = await ts.client()
+            assert cl.strategy.epoch_board is not None and list(cl.strategy.epoch_board[1].values()) == [1]
+        finally:
+            await ts.shutdown()
+
+    run(main())

@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 from enum import Enum, auto
 from itertools import product
 
-from torchstore_b200.rpc import Actor, endpoint
+from torchstore_b200.rpc import Actor, ActorMesh, endpoint
 from torchstore_b200.strategy import ControllerStorageVolumes, TorchStoreStrategy
 from torchstore_b200.transport.types import Request, TensorSlice
 
@@ -114,7 +114,8 @@ class Controller(Actor):
         slots = {vid: i + 1 for i, vid in enumerate(volume_ids)}
         try:
             for vid, slot in slots.items():
-                ref = self.storage_volumes.slice(**self.strategy.volume_id_to_coord[vid]) if hasattr(self.storage_volumes, "slice") \
+                # an ActorMesh is addressed by coordinate; ControllerStorageVolumes hands over one bare ref
+                ref = self.storage_volumes.slice(**self.strategy.volume_id_to_coord[vid]) if isinstance(self.storage_volumes, ActorMesh) \
                     else self.storage_volumes
                 ok = await ref.attach_epoch_board.call_one(board.name, slot)
                 if not ok:

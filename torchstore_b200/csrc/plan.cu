@@ -639,10 +639,15 @@ int tsb_plan_create(int device, const tsb_rect_t* rects, uint64_t n, uint32_t fl
     cudaError_t e = cudaMalloc(&p->d_block, p->layout.total);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host.data(), p->layout.total, cudaMemcpyHostToDevice, up);
     if (e == cudaSuccess) e = cudaStreamSynchronize(up);
+    // the events of tsb_plan_launch belong to the plan and exist from the start (no lazy creation that
+    // two threads launching the same plan could race on)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev_done);
     if (e != cudaSuccess) {
-      if (p->d_block) cudaFree(p->d_block);
-      delete p;
-      return cuda_fail(e, "plan upload");
+      cuda_fail(e, "plan upload");
+      free_plan(p);
+      return TSB_ERR_CUDA;
     }
   }
   PlanRegistry& reg = R();
@@ -685,11 +690,6 @@ int tsb_plan_launch_flags(tsb_plan_t plan, void* caller_stream, uint32_t flags) 
   if ((st = copy_stream(p->device, &s))) return st;
   DeviceGuard guard(p->device);
   if (!guard.ok) return cuda_fail(guard.err, "cudaSetDevice");
-  if (!p->ev_done) {
-    TSB_CUDA(cudaEventCreateWithFlags(&p->ev_fence, cudaEventDisableTiming));
-    TSB_CUDA(cudaEventCreate(&p->ev_start));
-    TSB_CUDA(cudaEventCreate(&p->ev_done));
-  }
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(caller_stream);
   if (cs) {
     TSB_CUDA(cudaEventRecord(p->ev_fence, cs));
