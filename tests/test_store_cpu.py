@@ -131,7 +131,7 @@ def test_hbm_tier_without_gpu_fails_loudly():
     run(main())
 
 
-@pytest.mark.parametrize("kind", ["Gloo", "MonarchRPC", "MonarchRDMA", "TorchComms"])
+@pytest.mark.parametrize("kind", ["Gloo", "MonarchRDMA", "TorchComms"])
 def test_other_transports_are_rejected(kind):
     async def main():
         await ts.initialize(num_storage_volumes=1, strategy=ts.ControllerStorageVolumes(getattr(ts.TransportType, kind)))
@@ -250,5 +250,41 @@ def test_rpc_errors_and_mesh():
             rpc.unregister_actor("t/b")
         with pytest.raises(rpc.ActorError, match="no actor named"):
             await a.add.call_one(1)
+
+    run(main())
+
+
+def test_by_value_actor_rpc_transport(monkeypatch):
+    """TransportType.MonarchRPC: payload rides the actor RPC (reference transport/monarch_rpc.py): tensors,
+    in-place and strided destinations, resharded gets across two volumes, objects."""
+    async def main():
+        await ts.initialize(num_storage_volumes=2, strategy=ts.LocalRankStrategy(ts.TransportType.MonarchRPC))
+        try:
+            t = torch.arange(96, dtype=torch.float32).reshape(8, 12)
+            await ts.put("t", t)
+            got = await ts.get("t")
+            assert torch.equal(got, t) and got.data_ptr() != t.data_ptr()
+            big = torch.zeros(10, 20)
+            out = await ts.get("t", big[1:9, 4:16])
+            assert torch.equal(big[1:9, 4:16], t) and out.data_ptr() == big[1:9, 4:16].data_ptr()
+            await ts.put("t", t + 1)                       # overwrite in place on the volume
+            assert torch.equal(await ts.get("t"), t + 1)
+            await ts.put_batch({"o": {"a": 1}, "u": torch.ones(3, dtype=torch.int64)})
+            assert (await ts.get_batch(["o", "u"]))["o"] == {"a": 1}
+            from torchstore_b200.transport import create_transport_buffer
+
+            for r in range(2):
+                monkeypatch.setenv("LOCAL_RANK", str(r))
+                cl = await ts.client()
+                req = Request.from_any("w", t[4 * r:4 * r + 4].contiguous(), TensorSlice((4 * r, 0), (r,), (8, 12), (4, 12), (2,)))
+                ref = cl.strategy.select_storage_volume()
+                await create_transport_buffer(ref).put_to_storage_volume([req])
+                await cl._controller.notify_put_batch.call([req.meta_only()], ref.volume_id)
+            assert torch.equal(await ts.get("w"), t)
+            col = torch.zeros(8, 6)
+            await ts.get("w", col, TensorSlice((0, 6), (1,), (8, 12), (8, 6), (2,)))
+            assert torch.equal(col, t[:, 6:])
+        finally:
+            await ts.shutdown()
 
     run(main())

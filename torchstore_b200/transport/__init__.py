@@ -1,7 +1,8 @@
-"""Transport registry.  The B200 build ships two tiers: the NVLink/HBM transport
+"""Transport registry.  The B200 build ships two data tiers: the NVLink/HBM transport
 (``transport/hbm.py``, the default wherever a CUDA device exists) and the host tier
 (``transport/host.py``: POSIX shm volumes for CPU clients and GPU-less boxes, the reference's
-``TransportType.SharedMemory``).  The enum keeps the reference's member names
+``TransportType.SharedMemory``), plus the by-value ``TransportType.MonarchRPC`` transport
+(``transport/actor_rpc.py``) for explicit use.  The enum keeps the reference's member names
 (transport/__init__.py:34-42) so existing ``Strategy(default_transport_type=...)`` call sites still
 import; selecting a transport that is not part of this build fails loudly instead of falling back."""
 
@@ -48,9 +49,15 @@ def create_transport_buffer(storage_volume_ref: "StorageVolumeRef") -> Transport
         from torchstore_b200.transport.host import HostShmTransportBuffer
 
         return HostShmTransportBuffer(storage_volume_ref)
+    if transport_type == TransportType.MonarchRPC:
+        # by value through the actor RPC: explicit choice only, never auto-selected
+        from torchstore_b200.transport.actor_rpc import ActorRpcTransportBuffer
+
+        return ActorRpcTransportBuffer(storage_volume_ref)
     raise RuntimeError(
         f"transport {transport_type.name} is not part of the B200 build; use TransportType.NVLink (HBM volumes), "
-        "TransportType.SharedMemory (host tier) or leave default_transport_type unset"
+        "TransportType.SharedMemory (host tier), TransportType.MonarchRPC (by value through the actor RPC) or leave "
+        "default_transport_type unset"
     )
 
 
