@@ -177,8 +177,11 @@ async def _get_state_dict_direct_rdma(store, key, user_state_dict):
     if key not in cache.handles:
         num_ranks = await store.get(f"{key}/num_ranks")
         all_handles = defaultdict(list)
+        # one batched fetch of every rank's handle table (the reference does num_ranks sequential gets,
+        # state_dict_utils.py:206-209); order by source rank is kept
+        tables = await store.get_batch([f"{key}/rank_{r}" for r in range(num_ranks)])
         for r in range(num_ranks):
-            for name, handle in (await store.get(f"{key}/rank_{r}")).items():
+            for name, handle in tables[f"{key}/rank_{r}"].items():
                 all_handles[name].append(handle)
         cache.handles[key] = all_handles
     await cache.dests[key].pull(cache.handles[key], user_state_dict)
