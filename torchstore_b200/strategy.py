@@ -78,29 +78,25 @@ class TorchStoreStrategy:
         raise NotImplementedError(f"{cls.__name__} must implement 'get_client_id'")
 
     async def set_storage_volumes(self, storage_volumes) -> None:
+        """Ask every volume of the mesh who it is: [(coord, (volume_id, hostname)), ...]."""
+        listing = await storage_volumes.get_id.call()
         self.storage_volumes = storage_volumes
-        self.volume_id_to_coord = {}
-        self.volume_id_to_hostname = {}
-        for coord, (volume_id, hostname) in await self.storage_volumes.get_id.call():
-            self.volume_id_to_coord[volume_id] = coord
-            self.volume_id_to_hostname[volume_id] = hostname
+        self.volume_id_to_coord = {vid: coord for coord, (vid, _host) in listing}
+        self.volume_id_to_hostname = {vid: host for _coord, (vid, host) in listing}
+
+    def _ref(self, actor, volume_id: str) -> StorageVolumeRef:
+        return StorageVolumeRef(actor, volume_id, self.transport_context, self.default_transport_type,
+                                volume_hostname=self.volume_id_to_hostname.get(volume_id),
+                                epoch_board=getattr(self, "epoch_board", None))
 
     def select_storage_volume(self) -> StorageVolumeRef:
-        client_id = self.get_client_id()  # client_id == volume_id for these strategies
-        if client_id not in self.volume_id_to_coord:
-            raise KeyError(f"No corresponding storage volume found for {client_id} {self.volume_id_to_coord=}")
-        return self.get_storage_volume(client_id)
+        mine = self.get_client_id()  # a client's id is the id of the volume it writes to
+        if mine not in self.volume_id_to_coord:
+            raise KeyError(f"No corresponding storage volume found for {mine} {self.volume_id_to_coord=}")
+        return self.get_storage_volume(mine)
 
     def get_storage_volume(self, volume_id: str) -> StorageVolumeRef:
-        coord = self.volume_id_to_coord[volume_id]
-        return StorageVolumeRef(
-            self.storage_volumes.slice(**coord),
-            volume_id,
-            self.transport_context,
-            self.default_transport_type,
-            volume_hostname=self.volume_id_to_hostname.get(volume_id),
-            epoch_board=getattr(self, "epoch_board", None),
-        )
+        return self._ref(self.storage_volumes.slice(**self.volume_id_to_coord[volume_id]), volume_id)
 
 
 class HostStrategy(TorchStoreStrategy):
@@ -141,12 +137,10 @@ class ControllerStorageVolumes(TorchStoreStrategy):
         return "0"
 
     async def set_storage_volumes(self, storage_volumes) -> None:
+        vid, host = await storage_volumes.get_id.call_one()
         self.storage_volumes = storage_volumes
-        self.volume_id_to_coord = {"0"}
-        self.volume_id_to_hostname = {}
-        volume_id, hostname = await self.storage_volumes.get_id.call_one()
-        self.volume_id_to_hostname[volume_id] = hostname
+        self.volume_id_to_coord = {"0": {}}  # one bare actor ref, no mesh coordinate
+        self.volume_id_to_hostname = {vid: host}
 
     def get_storage_volume(self, volume_id: str) -> StorageVolumeRef:
-        return StorageVolumeRef(self.storage_volumes, volume_id, self.transport_context, self.default_transport_type,
-                                volume_hostname=self.volume_id_to_hostname.get(volume_id))
+        return self._ref(self.storage_volumes, volume_id)
