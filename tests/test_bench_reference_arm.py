@@ -20,6 +20,8 @@ def test_reference_arm_prints_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["state_dict_bytes"] == 16060522496
+    gloo = d["cpu_baseline"]["gloo_transport"]  # the Gloo half of the reference's CPU transports, bounded sample
+    assert gloo is not None and (gloo.get("value", 0) > 0 or "unavailable" in gloo)
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
