@@ -118,15 +118,16 @@ def run_x2(args):
                         await sync.pull(handles, dest, dslices)
             torch.cuda.synchronize(0)
             torch.cuda.synchronize(1)
-            for sync in syncs:
+            active = syncs[:1] if args.solo else syncs   # --solo: GPU1 stays idle while GPU0 pulls from it
+            for sync in active:
                 sync.launch()
-            for sync in syncs:
+            for sync in active:
                 await sync.wait()
 
         for i in range(args.iters + 2):
             asyncio.run(both())
             if i >= 2:
-                times.append(max(s.last_pull_ms[own] for s, (own, *_r) in zip(syncs, sides)))
+                times.append(max(s.last_pull_ms[own] for s, (own, *_r) in list(zip(syncs, sides))[: 1 if args.solo else 2]))
         check_x2(sides)
         info = syncs[0].plan_info()[0]
         for s in syncs:
@@ -134,7 +135,7 @@ def run_x2(args):
         times.sort()
         med = times[len(times) // 2]
         local_read = info["src_bytes"] - info["remote_src_bytes"]
-        row = {"mode": f"x2_n{args.n}", "env": env, "ms_median": round(med, 4), "ms_min": round(times[0], 4),
+        row = {"mode": f"x2_n{args.n}" + ("_solo" if args.solo else ""), "env": env, "ms_median": round(med, 4), "ms_min": round(times[0], 4),
                "nvlink_in_GBps": round(info["remote_src_bytes"] / med / 1e6, 1),
                # HBM traffic of one GPU: own local reads + own writes + the peer's reads of our memory
                "hbm_GBps": round((local_read + info["payload_bytes"] + info["remote_src_bytes"]) / med / 1e6, 1),
@@ -160,6 +161,8 @@ def main():
     ap.add_argument("--env", default="", help="x2 mode: ';'-separated settings, each 'K=V,K=V' (empty = defaults)")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--solo", action="store_true",
+                    help="x2 mode: launch only GPU0's plan (its peer is idle): the kernel without source-side contention")
     ap.add_argument("--grid", default="2x65536,3x32768,3x65536,3x131072,4x32768,4x65536,4x131072,6x65536,8x32768,8x65536")
     args = ap.parse_args()
     _native.init()
