@@ -240,3 +240,19 @@ def test_segment_is_visible_to_another_process():
         _native.shm_unlink(name)
     with pytest.raises(_native.TsbError):
         _native.shm_attach(name, 4096)
+
+
+def test_put_batch_wait_false_on_the_host_tier_completes_inline():
+    """wait=False only returns early on the HBM fast lane; other tiers finish the put and hand back a
+    PendingPut that is already done (awaiting it is a no-op)."""
+    async def main():
+        await ts.initialize(num_storage_volumes=1, strategy=host_strategy())
+        try:
+            pending = await ts.put_batch({"a": torch.ones(4, 4), "o": {"k": 1}}, wait=False)
+            assert pending.done
+            await pending
+            assert torch.equal(await ts.get("a"), torch.ones(4, 4)) and await ts.get("o") == {"k": 1}
+        finally:
+            await ts.shutdown()
+
+    run(main())
