@@ -184,18 +184,6 @@ int tsb_plan_wait(tsb_plan_t plan);
 /* Device time of the last tsb_plan_launch (start event -> done event). */
 int tsb_plan_elapsed_ms(tsb_plan_t plan, float* out_ms);
 int tsb_plan_destroy(tsb_plan_t plan);
-/* EXPERIMENTAL (off unless called): tell a plan which blocks of ITS OWN GPU's memory the peers will read
- * while it runs (in symmetric syncs: this rank's source shards of the column-sharded params, in plan
- * order).  The link warps then prefetch that memory into the local L2 (UBLKPF.L2, evict-last), lead_bytes
- * ahead of their own progress through the link queue, so that the peers' NVLink reads hit L2 instead of
- * queueing behind this GPU's own HBM traffic.  n == 0 turns it off. */
-typedef struct tsb_stage_region {
-  uint64_t ptr;       /* device address on the plan's GPU, 16-byte aligned */
-  uint64_t row_bytes; /* contiguous bytes per row, multiple of 16 */
-  uint64_t pitch;     /* bytes between rows (== row_bytes for one contiguous block) */
-  uint64_t rows;
-} tsb_stage_region_t;
-int tsb_plan_set_stage(tsb_plan_t plan, const tsb_stage_region_t* regions, uint64_t n, uint64_t lead_bytes);
 /* Host-only (no CUDA call): compile and copy the kernel tables out, for inspection and for the
  * CPU test-suite, which replays them against the oracle.  out_rects: records of 192 bytes,
  * out_tiles: pairs of uint32 {rect, tile_in_rect}.  tile_units == 0 selects the default. */

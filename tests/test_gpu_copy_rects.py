@@ -264,39 +264,3 @@ def test_export_import_same_process_torch_suballocation():
     blob = _native.region_to_bytes(reg)
     assert len(blob) == 120 and _native.region_from_bytes(blob).offset == reg.offset
 
-
-@pytest.mark.parametrize("stream_policy", ["0", "1"])
-def test_experimental_l2_staging_and_stream_policy_do_not_change_results(stream_policy, monkeypatch):
-    """tsb_plan_set_stage (UBLKPF.L2 prefetches paced by the link queue) and the evict-first copy stream
-    (KIND_B16_STREAM) are performance hints: with them on, every byte still lands where it must."""
-    monkeypatch.setenv("TSB_LINK", "2")          # link queue on one GPU, so the staging code runs
-    monkeypatch.setenv("TSB_L2_STREAM", stream_policy)
-    g = torch.Generator(device="cuda").manual_seed(11)
-    src = torch.randint(-30000, 30000, (2048, 4096), dtype=torch.int16, device="cuda", generator=g)
-    served = torch.randint(-30000, 30000, (1024, 8192), dtype=torch.int16, device="cuda", generator=g)  # "what peers read"
-    served_before = served.clone()
-    dst = torch.zeros(2048, 512, dtype=torch.int16, device="cuda")
-    big_src = torch.randint(-30000, 30000, (1 << 22,), dtype=torch.int16, device="cuda", generator=g)
-    big_dst = torch.zeros_like(big_src)
-    rects, n = build_rects([(StridedMem.from_tensor(src[:, 1024:1536]), StridedMem.from_tensor(dst)),
-                            (StridedMem.from_tensor(big_src), StridedMem.from_tensor(big_dst))])
-    plan = _native.plan_create(0, rects, n)
-    info = _native.plan_info(plan)
-    assert info.num_link_tiles > 0
-    regions = [(served.data_ptr(), served.numel() * 2, served.numel() * 2, 1),            # one contiguous block
-               (served.data_ptr() + 2048, 1024, 16384, 1024),                             # a column block, row by row
-               (src.data_ptr(), 8192, 8192, 2048)]
-    for lead in (0, 1 << 20, 64 << 20):
-        _native.plan_set_stage(plan, regions, lead)
-        dst.zero_()
-        big_dst.zero_()
-        for _ in range(2):
-            _native.plan_launch(plan, _native.torch_stream(0))
-            _native.plan_wait(plan)
-        assert torch.equal(dst, src[:, 1024:1536]) and torch.equal(big_dst, big_src) and torch.equal(served, served_before)
-    _native.plan_set_stage(plan, [], 0)  # off again
-    _native.plan_launch(plan, None)
-    _native.plan_wait(plan)
-    with pytest.raises(_native.TsbError):
-        _native.plan_set_stage(plan, [(src.data_ptr() + 2, 16, 16, 1)], 0)  # misaligned region
-    _native.plan_destroy(plan)

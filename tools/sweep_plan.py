@@ -116,25 +116,6 @@ def run_x2(args):
                 if sync._plan is None:
                     with torch.cuda.device(own):
                         await sync.pull(handles, dest, dslices)
-            if os.environ.get("TSB_STAGE") == "1" and not getattr(syncs[0], "_staged", False):
-                # each GPU stages exactly what the OTHER side's plan reads from it, in that plan's order
-                for i, sync in enumerate(syncs):
-                    own = sides[i][0]
-                    other = syncs[1 - i]
-                    regions = []
-                    for op in other._plan:
-                        win = op.rdma_buffer.window(sides[1 - i][0])
-                        if win.device != own:
-                            continue
-                        src, _ = DirectWeightSyncDest.op_windows(op, win)
-                        isz = src.itemsize
-                        if len(src.shape) == 2 and src.stride[1] == 1:
-                            regions.append((src.ptr, src.shape[1] * isz, src.stride[0] * isz, src.shape[0]))
-                        elif src.is_contiguous():
-                            nb = src.numel * isz
-                            regions.append((src.ptr, nb, nb, 1))
-                    sync.set_stage(own, [r for r in regions if r[1] % 16 == 0 and r[0] % 16 == 0])
-                    sync._staged = True
             torch.cuda.synchronize(0)
             torch.cuda.synchronize(1)
             active = syncs[:1] if args.solo else syncs   # --solo: GPU1 stays idle while GPU0 pulls from it

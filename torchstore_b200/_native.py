@@ -118,7 +118,6 @@ _SIGNATURES = {
     "tsb_plan_poll": (C.c_int, [C.c_uint64, C.POINTER(C.c_int)]),
     "tsb_plan_wait": (C.c_int, [C.c_uint64]),
     "tsb_plan_elapsed_ms": (C.c_int, [C.c_uint64, C.POINTER(C.c_float)]),
-    "tsb_plan_set_stage": (C.c_int, [C.c_uint64, _vp, C.c_uint64, C.c_uint64]),
     "tsb_plan_destroy": (C.c_int, [C.c_uint64]),
     "tsb_pool_stats": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tsb_plan_compile_host": (
@@ -330,18 +329,6 @@ def plan_elapsed_ms(plan: int) -> float:
     ms = C.c_float(0)
     check(lib().tsb_plan_elapsed_ms(plan, C.byref(ms)))
     return float(ms.value)
-
-
-class StageRegionStruct(C.Structure):
-    _fields_ = [("ptr", C.c_uint64), ("row_bytes", C.c_uint64), ("pitch", C.c_uint64), ("rows", C.c_uint64)]
-
-
-def plan_set_stage(plan: int, regions: list[tuple[int, int, int, int]], lead_bytes: int) -> None:
-    """EXPERIMENTAL: (ptr, row_bytes, pitch, rows) blocks of the plan's own GPU that peers read while it runs."""
-    arr = (StageRegionStruct * max(1, len(regions)))()
-    for i, (ptr, row_bytes, pitch, rows) in enumerate(regions):
-        arr[i].ptr, arr[i].row_bytes, arr[i].pitch, arr[i].rows = ptr, row_bytes, pitch, rows
-    check(lib().tsb_plan_set_stage(plan, C.cast(arr, C.c_void_p), len(regions), lead_bytes))
 
 
 def plan_destroy(plan: int) -> None:

@@ -57,35 +57,7 @@ struct MoveB16T {
   static __device__ __forceinline__ Reg ld(const char* p) { return ldg16(p); }
   static __device__ __forceinline__ void st(char* p, const Reg& v) { stg16(p, v); }
 };
-// Same data path with an L2 evict-first policy on every access: the stream never re-reads a line, so it
-// should be the first thing L2 drops -- which keeps lines staged for the peers (UBLKPF.L2, evict-last) alive.
-struct MoveB16Stream {
-  static constexpr int kUnroll = 4;
-  using Reg = uint4;
-  static __device__ __forceinline__ uint64_t policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-  }
-  static __device__ __forceinline__ Reg ld(const char* p) {
-    uint4 v;
-    const uint64_t pol = policy();
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-  }
-  static __device__ __forceinline__ void st(char* p, const Reg& v) {
-    const uint64_t pol = policy();
-    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w), "l"(pol)
-                 : "memory");
-  }
-};
 using MoveB16 = MoveB16T<4>;
-// Half the loads in flight per thread: used when the launch shares HBM with peers pulling from it
-// (a shallower local queue keeps the latency of the served NVLink reads down)
-using MoveB16Shallow = MoveB16T<2>;
 template <typename T>
 struct MoveSmall {
   static constexpr int kUnroll = 4;
@@ -305,21 +277,12 @@ __device__ __forceinline__ void move_tile(const DevRect& r, uint32_t tile_in_rec
 // KIND selects a kernel specialisation chosen by the plan compiler:
 //   KIND_GENERIC  any mix of modes (per-tile dispatch, out-of-line movers)
 //   KIND_B16      every rect moves 16-byte units: the weight-sync case, fully inlined
-//   KIND_B16_SHALLOW  same, 2 instead of 4 loads in flight per thread
 //   KIND_F32_BF16 every rect is the vector fp32->bf16 cast (transfer_dtype=bf16), fully inlined
 template <int KIND>
 __device__ __forceinline__ void process_tile(const DevRect& r, uint32_t tile_in_rect) {
   const uint32_t tile_units = r.tile_units;
   if (KIND == KIND_B16) {
     move_tile<MoveB16, true>(r, tile_in_rect, tile_units);
-    return;
-  }
-  if (KIND == KIND_B16_SHALLOW) {
-    move_tile<MoveB16Shallow, true>(r, tile_in_rect, tile_units);
-    return;
-  }
-  if (KIND == KIND_B16_STREAM) {
-    move_tile<MoveB16Stream, true>(r, tile_in_rect, tile_units);
     return;
   }
   if (KIND == KIND_F32_BF16) {
@@ -435,49 +398,12 @@ __device__ __forceinline__ void link_warp_run(const LaunchParams& p, unsigned ch
     ++stored;
   };
 
-  // L2 staging (experimental, TSB_STAGE): every claimed batch of link tiles also prefetches the matching slice of
-  // the memory THIS GPU serves to its peers (p.stage, in the order the symmetric peers read it), a fixed lead ahead
-  // of the claim.  Claims are unique, so every staged byte is prefetched exactly once per launch.
-  uint64_t stage_policy = 0;
-  if (p.num_stage) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(stage_policy));
-  auto stage_slice = [&](uint64_t tile_lo, uint64_t tile_hi) {
-    uint64_t o0 = min(tile_lo * p.stage_units_per_tile, p.stage_total_units) * 16;
-    uint64_t o1 = min(tile_hi * p.stage_units_per_tile, p.stage_total_units) * 16;
-    if (o0 >= o1) return;
-    for (uint32_t i = lane; i < p.num_stage; i += kLinkThreads) {
-      const StageRegion g = p.stage[i];
-      const uint64_t total = g.rows * g.row_bytes;
-      uint64_t lo = max(o0, g.prefix), hi = min(o1, g.prefix + total);
-      if (lo >= hi) continue;
-      lo -= g.prefix;
-      hi -= g.prefix;
-      if (g.pitch == g.row_bytes) {  // one contiguous block
-        const uint32_t bytes = static_cast<uint32_t>(hi - lo);
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(g.ptr + lo), "r"(bytes), "l"(stage_policy)
-                     : "memory");
-        continue;
-      }
-      while (lo < hi) {  // row by row (column block of a wider tensor)
-        const uint64_t row = lo / g.row_bytes, col = lo - row * g.row_bytes;
-        const uint32_t bytes = static_cast<uint32_t>(min(g.row_bytes - col, hi - lo));
-        asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(g.ptr + row * g.pitch + col), "r"(bytes),
-                     "l"(stage_policy)
-                     : "memory");
-        lo += bytes;
-      }
-    }
-  };
-
   uint32_t base = 0;
   if (lane == 0) base = atomicAdd(p.sched + 2, kLinkBatch);
   base = __shfl_sync(0xffffffffu, base, 0);
   while (base < n) {
     uint32_t next_base = 0;
     if (lane == 0) next_base = atomicAdd(p.sched + 2, kLinkBatch);  // consumed after this batch: latency hidden
-    if (p.num_stage) {
-      if (base < p.stage_lead_tiles) stage_slice(base, min(static_cast<uint64_t>(base) + kLinkBatch, static_cast<uint64_t>(p.stage_lead_tiles)));  // the first window
-      stage_slice(static_cast<uint64_t>(base) + p.stage_lead_tiles, static_cast<uint64_t>(base) + p.stage_lead_tiles + kLinkBatch);
-    }
     const uint32_t cnt = min(kLinkBatch, n - base);
     DevTile mine{0u, 0u};
     if (lane < cnt) mine = p.link_tiles[base + lane];
@@ -646,8 +572,6 @@ int max_ctas_per_sm(uint32_t kind, bool with_link, uint32_t link_smem_bytes, int
   const uint32_t smem = with_link ? link_smem_bytes : 0u;
   switch (kind) {
     case KIND_B16: e = occupancy<KIND_B16>(with_link, smem, &n); break;
-    case KIND_B16_SHALLOW: e = occupancy<KIND_B16_SHALLOW>(with_link, smem, &n); break;
-    case KIND_B16_STREAM: e = occupancy<KIND_B16_STREAM>(with_link, smem, &n); break;
     case KIND_F32_BF16: e = occupancy<KIND_F32_BF16>(with_link, smem, &n); break;
     default: e = occupancy<KIND_GENERIC>(with_link, smem, &n); break;
   }
@@ -667,8 +591,6 @@ int launch_copy_rects(const LaunchParams& p, uint32_t grid, cudaStream_t stream)
   cudaError_t e;
   switch (p.kind) {
     case KIND_B16: e = launch<KIND_B16>(p, grid, stream); break;
-    case KIND_B16_SHALLOW: e = launch<KIND_B16_SHALLOW>(p, grid, stream); break;
-    case KIND_B16_STREAM: e = launch<KIND_B16_STREAM>(p, grid, stream); break;
     case KIND_F32_BF16: e = launch<KIND_F32_BF16>(p, grid, stream); break;
     default: e = launch<KIND_GENERIC>(p, grid, stream); break;
   }

@@ -53,12 +53,6 @@ struct Plan {
   // fenced launches (tsb_plan_launch): created on first use, reused every sync
   cudaEvent_t ev_fence = nullptr, ev_start = nullptr, ev_done = nullptr;
   bool launched = false;
-  // L2 staging of served memory (tsb_plan_set_stage)
-  StageRegion* d_stage = nullptr;
-  uint32_t num_stage = 0;
-  uint64_t stage_total_units = 0;
-  uint32_t stage_units_per_tile = 0;
-  uint32_t stage_lead_tiles = 0;
 };
 
 // Recycled {pinned host, device} table buffers for one-shot copies (tsb_copy_rects): the tables
@@ -311,11 +305,7 @@ struct Compiler {
       all_b16 = all_b16 && r.mode == MODE_B16;
       all_cast = all_cast && r.mode == MODE_F32_BF16_V8;
     }
-    if (all_b16) {
-      if (env_u32("TSB_L2_STREAM", 0)) return KIND_B16_STREAM;  // evict-first on the copy warps' stream (experiment)
-      return env_u32("TSB_COPY_UNROLL", 4) == 2 ? KIND_B16_SHALLOW : KIND_B16;
-    }
-    return all_cast ? KIND_F32_BF16 : KIND_GENERIC;
+    return all_b16 ? KIND_B16 : all_cast ? KIND_F32_BF16 : KIND_GENERIC;
   }
 
   // Tile order of one queue: proportional interleave over source devices, starting after the
@@ -477,7 +467,6 @@ void free_plan(Plan* p) {
   if (p->ev_fence) cudaEventDestroy(p->ev_fence);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
   if (p->ev_done) cudaEventDestroy(p->ev_done);
-  if (p->d_stage) cudaFree(p->d_stage);
   if (p->d_block) cudaFree(p->d_block);  // synchronises with outstanding work that uses the tables
   delete p;
 }
@@ -550,13 +539,6 @@ int run_plan(Plan* p, cudaStream_t s) {
   if (getenv("TSB_FORCE_GENERIC")) kind = KIND_GENERIC;
   LaunchParams lp = make_params(p->d_block, p->layout, p->num_tiles, p->num_link_tiles, kind, p->link_stage_bytes, p->link_stages);
   if (getenv("TSB_STATIC_SCHED") && p->num_link_tiles == 0) lp.sched = nullptr;
-  if (p->num_stage && p->num_link_tiles) {
-    lp.stage = p->d_stage;
-    lp.num_stage = p->num_stage;
-    lp.stage_total_units = p->stage_total_units;
-    lp.stage_units_per_tile = p->stage_units_per_tile;
-    lp.stage_lead_tiles = p->stage_lead_tiles;
-  }
   return launch_copy_rects(lp, p->info.grid, s);
 }
 
@@ -760,43 +742,6 @@ int tsb_plan_elapsed_ms(tsb_plan_t plan, float* out_ms) {
   if (st) return st;
   if (!p->launched) return fail(TSB_ERR_INVALID, "plan was never launched with tsb_plan_launch");
   TSB_CUDA(cudaEventElapsedTime(out_ms, p->ev_start, p->ev_done));
-  return TSB_OK;
-}
-
-int tsb_plan_set_stage(tsb_plan_t plan, const tsb_stage_region_t* regions, uint64_t n, uint64_t lead_bytes) {
-  Plan* p;
-  int st = find_plan(plan, &p);
-  if (st) return st;
-  if (n && !regions) return fail(TSB_ERR_INVALID, "regions is NULL");
-  DeviceGuard guard(p->device);
-  if (!guard.ok) return cuda_fail(guard.err, "cudaSetDevice");
-  if (p->d_stage) {
-    cudaFree(p->d_stage);  // synchronises with launches that still read it
-    p->d_stage = nullptr;
-  }
-  p->num_stage = 0;
-  if (n == 0 || p->num_link_tiles == 0) return TSB_OK;
-  std::vector<StageRegion> host;
-  uint64_t prefix = 0;
-  for (uint64_t i = 0; i < n; ++i) {
-    const tsb_stage_region_t& r = regions[i];
-    if (!r.ptr || r.ptr % 16 || r.row_bytes % 16 || r.pitch % 16 || r.pitch < r.row_bytes)
-      return fail(TSB_ERR_INVALID, "stage region: 16-byte aligned ptr/row_bytes/pitch and pitch >= row_bytes required");
-    if (!r.rows || !r.row_bytes) continue;
-    host.push_back({r.ptr, r.row_bytes, r.pitch, r.rows, prefix});
-    prefix += r.rows * r.row_bytes;
-  }
-  if (host.empty()) return TSB_OK;
-  cudaStream_t up;
-  if ((st = copy_stream(p->device, &up))) return st;
-  cudaError_t e = cudaMalloc(&p->d_stage, host.size() * sizeof(StageRegion));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_stage, host.data(), host.size() * sizeof(StageRegion), cudaMemcpyHostToDevice, up);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(up);
-  if (e != cudaSuccess) return cuda_fail(e, "stage upload");
-  p->num_stage = static_cast<uint32_t>(host.size());
-  p->stage_total_units = prefix / 16;
-  p->stage_units_per_tile = static_cast<uint32_t>((p->stage_total_units + p->num_link_tiles - 1) / p->num_link_tiles);
-  p->stage_lead_tiles = static_cast<uint32_t>(std::min<uint64_t>(lead_bytes / std::max<uint32_t>(p->link_stage_bytes, 16u), p->num_link_tiles));
   return TSB_OK;
 }
 

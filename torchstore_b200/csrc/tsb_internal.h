@@ -98,17 +98,7 @@ struct DevTile {
 };
 
 // kernel specialisations (see copy_rects.cu)
-enum : uint32_t { KIND_GENERIC = 0, KIND_B16 = 1, KIND_F32_BF16 = 2, KIND_B16_SHALLOW = 3, KIND_B16_STREAM = 4 };
-
-// A block of THIS GPU's memory that peers will read during the launch ("serve list", experimental):
-// the link warps prefetch it into the local L2 just ahead of the peers' reads.
-struct StageRegion {
-  uint64_t ptr;
-  uint64_t row_bytes;  // multiple of 16
-  uint64_t pitch;
-  uint64_t rows;
-  uint64_t prefix;     // payload bytes (rows x row_bytes) of all regions before this one
-};
+enum : uint32_t { KIND_GENERIC = 0, KIND_B16 = 1, KIND_F32_BF16 = 2 };
 
 // Two work queues per plan (see copy_rects.cu):
 //   copy queue  tiles moved by the CTA's 8 copy warps with LDG.128/STG.128 (local HBM sources,
@@ -126,13 +116,6 @@ struct LaunchParams {
   uint32_t link_stage_bytes;  // bytes per ring stage (== tile size of link rects)
   uint32_t link_stages;       // ring depth S
   uint32_t link_lag;          // stores trail loads by this many stages (< S)
-  // L2 staging of served memory (see StageRegion): stage_units_per_tile 16-byte units are prefetched per
-  // link tile of progress, stage_lead_tiles ahead of the claim
-  const StageRegion* stage;
-  uint32_t num_stage;
-  uint32_t stage_units_per_tile;
-  uint32_t stage_lead_tiles;
-  uint64_t stage_total_units;
   uint32_t* sched;  // {copy claim, finished CTAs, link claim, pad}; nullptr = fully static striding (no link queue)
 };
 

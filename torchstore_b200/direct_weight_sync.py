@@ -29,7 +29,6 @@ from __future__ import annotations
 
 import asyncio
 import logging
-import os
 import threading
 from collections import defaultdict
 from dataclasses import dataclass
@@ -404,40 +403,6 @@ class DirectWeightSyncDest:
         for dev, pairs in per_device.items():
             rects, n = build_rects(pairs)
             self._native_plans[dev] = _native.plan_create(dev, rects, n)
-        if os.environ.get("TORCHSTORE_B200_STAGE", "0") == "1":
-            self._stage_symmetric()
-
-    # -- EXPERIMENTAL: L2 staging of the memory this GPU serves to its peers -------------------------------
-    def set_stage(self, dev: int, regions: list[tuple[int, int, int, int]], lead_bytes: int | None = None) -> None:
-        """Tell the plan of ``dev`` which (ptr, row_bytes, pitch, rows) blocks of that GPU's memory the peers
-        read while it runs, in the order they read them (tsb_plan_set_stage).  Empty list: off."""
-        if lead_bytes is None:
-            lead_bytes = int(os.environ.get("TSB_STAGE_LEAD_BYTES", 8 << 20))
-        _native.plan_set_stage(self._native_plans[dev], regions, lead_bytes)
-
-    def _stage_symmetric(self) -> None:
-        """Symmetric syncs (every rank is source and destination, same destination layout on every rank):
-        wherever THIS rank reads only a column block of one of its own source shards, its peers read the
-        other column blocks of the same shard at the same point of their plans -- so the whole shard is
-        what this GPU serves, in plan order."""
-        per_device: dict[int, list] = defaultdict(list)
-        seen = set()
-        for op in self._plan:
-            if op.dest_tensor is None:
-                continue
-            dev = op.dest_local.device.index
-            win = op.rdma_buffer.window(dev)
-            if win.device != dev or win.ptr in seen or not win.is_contiguous():
-                continue
-            src, _ = self.op_windows(op, win)
-            if src.numel * src.itemsize >= win.numel * win.itemsize:
-                continue  # reads its whole shard: nothing left for the peers
-            seen.add(win.ptr)
-            nbytes = win.numel * win.itemsize // 16 * 16
-            per_device[dev].append((win.ptr, nbytes, nbytes, 1))
-        for dev, regions in per_device.items():
-            if dev in self._native_plans and regions:
-                self.set_stage(dev, regions)
 
     def plan_info(self) -> dict[int, dict]:
         return {dev: _native.plan_info(p).as_dict() for dev, p in self._native_plans.items()}
