@@ -1,6 +1,7 @@
 """Grid of launch settings for the 2-GPU emulation of the N-rank sync (tools/sweep_plan.py --mode x2):
 link queue on/off x CTAs per SM x loads in flight per thread x ring geometry.  Prints the env string
-for --env."""
+for --env.  (TSB_COPY_UNROLL was a knob of the round-2 experiment builds -- 2 loads in flight per copy
+thread measured no gain and was removed; the shipped library ignores it.)"""
 import itertools
 import sys
 

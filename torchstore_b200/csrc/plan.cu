@@ -457,7 +457,6 @@ LaunchParams make_params(char* d_block, const TableLayout& l, uint32_t n_tiles, 
   lp.kind = kind;
   lp.link_stage_bytes = link_stage_bytes;
   lp.link_stages = link_stages;
-  lp.link_lag = link_stages >= 2 ? link_stages - 2 : 0;
   lp.sched = reinterpret_cast<uint32_t*>(d_block);
   return lp;
 }

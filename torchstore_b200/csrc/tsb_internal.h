@@ -114,8 +114,7 @@ struct LaunchParams {
   uint32_t num_link_tiles;
   uint32_t kind;
   uint32_t link_stage_bytes;  // bytes per ring stage (== tile size of link rects)
-  uint32_t link_stages;       // ring depth S
-  uint32_t link_lag;          // stores trail loads by this many stages (< S)
+  uint32_t link_stages;       // ring depth S (stores trail loads by S-2 stages)
   uint32_t* sched;  // {copy claim, finished CTAs, link claim, pad}; nullptr = fully static striding (no link queue)
 };
 
