@@ -310,3 +310,33 @@ def test_plan_rebuilt_when_destination_changes():
     d2 = torch.zeros(64, 64, device=DEV)
     run(sync.pull({"w": [handles["w"]]}, {"w": d2}))
     assert torch.equal(d1, w) and torch.equal(d2, w)
+
+
+def test_same_dict_pull_launches_first_and_still_catches_in_place_edits():
+    """Passing the very dict object of the last pull launches the cached plan before validating it; an
+    edit of that dict in between (a value replaced, or a tensor's storage swapped under the same object)
+    is caught while the kernel runs and the pull is redone into the right memory."""
+    w = torch.randn(256, 128, device=DEV)
+    b = torch.randn(128, device=DEV)
+    handles = DirectWeightSyncSource().register({"w": w, "b": b}, rank=0)
+    hs = {"w": [handles["w"]], "b": [handles["b"]]}
+    dest = {"w": torch.zeros(256, 128, device=DEV), "b": torch.zeros(128, device=DEV)}
+    sync = DirectWeightSyncDest()
+    run(sync.pull(hs, dest))
+    plan0 = dict(sync._native_plans)
+    w.add_(1.0)
+    torch.cuda.synchronize()
+    run(sync.pull(hs, dest))                      # same dict object, nothing edited: cached plan replayed
+    assert sync._native_plans == plan0 and torch.equal(dest["w"], w)
+    old_w = dest["w"]
+    dest["w"] = torch.zeros(256, 128, device=DEV)  # value replaced inside the same dict
+    run(sync.pull(hs, dest))
+    assert torch.equal(dest["w"], w) and sync._native_plans != plan0
+    assert torch.equal(old_w, w)                   # the speculative launch filled the old tensor: harmless
+    plan1 = dict(sync._native_plans)
+    dest["b"].data = torch.zeros(128, device=DEV)  # same object, other storage
+    b.mul_(3.0)
+    torch.cuda.synchronize()
+    run(sync.pull(hs, dest))
+    assert torch.equal(dest["b"], b) and sync._native_plans != plan1
+    sync.close()

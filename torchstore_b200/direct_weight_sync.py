@@ -312,6 +312,7 @@ class DirectWeightSyncDest:
         self._plan_signature: tuple | None = None
         self._plan_ids: tuple | None = None  # id() of the destination objects the plan was built for
         self._plan_refs: list | None = None  # ...kept alive, so those ids cannot be recycled
+        self._plan_dict: dict | None = None  # the dict object they came in (identity short-cut of the next pull)
         self._native_plans: dict[int, int] = {}  # device -> plan id
         self.last_pull_ms: dict[int, float] = {}  # device -> kernel time of the last pull
 
@@ -418,6 +419,17 @@ class DirectWeightSyncDest:
         against the destination OBJECTS first (their ids; the plan keeps them alive), the kernel
         is enqueued, and the data-pointer signature -- which catches ``param.data = new`` under an
         unchanged object -- is recomputed while the kernel runs."""
+        if self._plan is not None and dest_state_dict is self._plan_dict:
+            # the very dict object of the last pull: launch first, validate it (object ids, then data pointers)
+            # while the kernel runs -- a stale launch only fills memory the plan still references
+            self.launch()
+            same = tuple(map(id, dest_state_dict.values())) == self._plan_ids and \
+                self._signature(dest_state_dict) == self._plan_signature
+            await self.wait()
+            if same:
+                return
+            logger.info("destination dict was edited in place; rebuilding the transfer plan")
+            self.close()
         ids = tuple(map(id, dest_state_dict.values()))
         verified = False
         if self._plan is not None and ids != self._plan_ids:
@@ -426,13 +438,13 @@ class DirectWeightSyncDest:
                 logger.info("destination tensors changed; rebuilding the transfer plan")
                 self.close()
             else:
-                self._plan_ids, self._plan_refs = ids, list(dest_state_dict.values())
+                self._plan_ids, self._plan_refs, self._plan_dict = ids, list(dest_state_dict.values()), dest_state_dict
             verified = True
         if self._plan is None:
             self._plan = self._build_plan(all_handles, dest_state_dict, dest_slices)
             self._compile()
             self._plan_signature = self._signature(dest_state_dict)
-            self._plan_ids, self._plan_refs = ids, list(dest_state_dict.values())
+            self._plan_ids, self._plan_refs, self._plan_dict = ids, list(dest_state_dict.values()), dest_state_dict
             verified = True
         self.launch()
         stale = not verified and self._signature(dest_state_dict) != self._plan_signature
@@ -464,7 +476,7 @@ class DirectWeightSyncDest:
                 logger.warning("plan_destroy failed: %s", e)
         self._native_plans = {}
         self._plan = None
-        self._plan_ids = self._plan_refs = None
+        self._plan_ids = self._plan_refs = self._plan_dict = None
 
 
 def _contig(shape) -> tuple:

@@ -114,7 +114,9 @@ async def _put_state_dict_direct_rdma(store, state_dict, key, transfer_dtype=Non
     cache = _get_rdma_cache(store)
     # one source object per key: the reference keeps a single one per client, whose handles and
     # staging buffers are overwritten when a second key is registered (state_dict_utils.py:171-178)
-    cache.source = cache.sources.setdefault(key, DirectWeightSyncSource())
+    cache.source = cache.sources.get(key)
+    if cache.source is None:
+        cache.source = cache.sources[key] = DirectWeightSyncSource()
     if key not in cache.registered:
         assert state_dict is not None, "state_dict is required on first put_state_dict call with direct_rdma=True"
         rank, world_size = dist.get_rank(), dist.get_world_size()
@@ -171,7 +173,9 @@ async def _get_state_dict_direct_rdma(store, key, user_state_dict):
     # one destination object (= one cached transfer plan) per state-dict key; the reference keeps a
     # single one per client (state_dict_utils.py:198-201), which silently replays the first key's plan
     # for every later key
-    cache.dest = cache.dests.setdefault(key, DirectWeightSyncDest())
+    cache.dest = cache.dests.get(key)
+    if cache.dest is None:
+        cache.dest = cache.dests[key] = DirectWeightSyncDest()
     if allgather_enabled() and _try_all_gather(cache, key, user_state_dict):
         return
     if key not in cache.handles:
