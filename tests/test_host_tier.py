@@ -256,3 +256,74 @@ def test_put_batch_wait_false_on_the_host_tier_completes_inline():
             await ts.shutdown()
 
     run(main())
+
+
+# ---- the reference's own results as the oracle for the host tiers ---------------------------------------
+import hashlib
+import itertools
+import json
+
+import numpy as np
+
+from oracle import reshard_oracle as ro
+from torchstore_b200.transport import create_transport_buffer
+from torchstore_b200.transport.types import Request
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _sha(t):
+    return hashlib.sha256(t.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("transport", ["SharedMemory", "MonarchRPC"])
+def test_reshard_matrix_matches_the_reference_results_on_the_host_tiers(transport, monkeypatch):
+    """tests/golden/store_reshard.json holds sha256 of what the UNMODIFIED reference (LocalClient +
+    SharedMemory transport, run by oracle/gen_golden.py) returned for a matrix of source/destination
+    meshes and placements; the host tier and the by-value transport must return the same bytes."""
+    gold = json.load(open(os.path.join(GOLDEN, "store_reshard.json")))
+    ttype = getattr(ts.TransportType, transport)
+
+    async def put_shard(rank, key, local, tslice):
+        monkeypatch.setenv("LOCAL_RANK", str(rank))
+        c = await ts.client()
+        req = Request(key=key, tensor_val=local, tensor_slice=tslice)
+        ref = c.strategy.select_storage_volume()
+        await create_transport_buffer(ref).put_to_storage_volume([req])
+        await c._controller.notify_put_batch.call([req.meta_only()], ref.volume_id)
+
+    async def main():
+        for case in gold["cases"]:
+            shape = tuple(case["global_shape"])
+            full = torch.arange(int(np.prod(shape)), dtype=torch.float32).reshape(shape)
+            smesh, dmesh = tuple(case["src_mesh"]), tuple(case["dst_mesh"])
+            spl = [tuple(p) for p in case["src_placements"]]
+            dpl = [tuple(p) for p in case["dst_placements"]]
+            nvol = max(int(np.prod(smesh)), int(np.prod(dmesh)))
+            await ts.initialize(num_storage_volumes=nvol, strategy=ts.LocalRankStrategy(ttype))
+            try:
+                all_rep = all(p[0] == "R" for p in spl)
+                for rank, coord in enumerate(itertools.product(*(range(m) for m in smesh))):
+                    sl = ro.make_slice(shape, smesh, coord, spl)
+                    local = full[tuple(slice(o, o + s) for o, s in zip(sl.offsets, sl.local_shape))].contiguous()
+                    if all_rep:
+                        monkeypatch.setenv("LOCAL_RANK", str(rank))
+                        await ts.put("test_key", local)
+                    else:
+                        await put_shard(rank, "test_key", local,
+                                        TensorSlice(sl.offsets, sl.coordinates, sl.global_shape, sl.local_shape, sl.mesh_shape))
+                for r in case["per_rank"]:
+                    coord = list(itertools.product(*(range(m) for m in dmesh)))[r["rank"]]
+                    dsl = ro.make_slice(shape, dmesh, coord, dpl)
+                    dest = torch.zeros(dsl.local_shape, dtype=torch.float32)
+                    monkeypatch.setenv("LOCAL_RANK", str(r["rank"]))
+                    got = await ts.get("test_key", dest, TensorSlice(dsl.offsets, dsl.coordinates, dsl.global_shape,
+                                                                     dsl.local_shape, dsl.mesh_shape))
+                    assert got is dest
+                    assert _sha(dest) == r["sha256"], (transport, case["src_mesh"], case["dst_mesh"], r["rank"])
+                assert _sha(await ts.get("test_key")) == case["full_get_sha256"]
+            finally:
+                await ts.shutdown()
+
+    run(main())
+    assert not _segments()
