@@ -19,6 +19,7 @@ GET  the volume returns descriptors of the stored views; the client copies segme
 
 from __future__ import annotations
 
+import bisect
 import ctypes
 import logging
 import os
@@ -111,6 +112,8 @@ class HostVolumeCache(TransportCache):
         self.segments: dict[str, _Segment] = {}
         self._storage_refs: dict[str, weakref.ref] = {}  # segment name -> weakref on the stored tensor's storage
         self._pending: dict = {}
+        self._starts: list[int] = []                     # sorted base addresses of our segments (describe() bisects)
+        self._by_start: dict[int, _Segment] = {}
 
     def allocate(self, shape, dtype: torch.dtype) -> tuple[torch.Tensor, ShmDescriptor]:
         numel = 1
@@ -122,6 +125,8 @@ class HostVolumeCache(TransportCache):
             name = f"/tsb200_{os.getpid()}_{_seq[0]}_{os.urandom(3).hex()}"
         ptr = _native.shm_create(name, nbytes)
         seg = self.segments[name] = _Segment(name, ptr, nbytes, owner=True)
+        bisect.insort(self._starts, ptr)
+        self._by_start[ptr] = seg
         seg.pin()
         stride, s = [], 1
         for e in reversed(shape):
@@ -138,16 +143,26 @@ class HostVolumeCache(TransportCache):
         self._storage_refs.pop(name, None)
         seg = self.segments.pop(name, None)
         if seg is not None:
+            self._forget_start(seg.ptr)
             seg.close()
+
+    def _forget_start(self, ptr: int) -> None:
+        self._by_start.pop(ptr, None)
+        i = bisect.bisect_left(self._starts, ptr)
+        if i < len(self._starts) and self._starts[i] == ptr:
+            del self._starts[i]
 
     def describe(self, tensor: torch.Tensor) -> ShmDescriptor | None:
         """Descriptor of a stored tensor or of a view of one (None: not backed by our segments)."""
         ptr = tensor.data_ptr()
-        for seg in self.segments.values():
-            if seg.ptr <= ptr < seg.ptr + seg.nbytes:
-                off = (ptr - seg.ptr) // tensor.element_size()
-                return ShmDescriptor(seg.name, seg.nbytes, tuple(tensor.shape), tuple(tensor.stride()), tensor.dtype, off)
-        return None
+        i = bisect.bisect_right(self._starts, ptr) - 1
+        if i < 0:
+            return None
+        seg = self._by_start[self._starts[i]]
+        if not (seg.ptr <= ptr < seg.ptr + seg.nbytes):
+            return None
+        off = (ptr - seg.ptr) // tensor.element_size()
+        return ShmDescriptor(seg.name, seg.nbytes, tuple(tensor.shape), tuple(tensor.stride()), tensor.dtype, off)
 
     def clear(self) -> None:
         self._pending.clear()
@@ -155,6 +170,8 @@ class HostVolumeCache(TransportCache):
         for seg in self.segments.values():
             seg.close()
         self.segments.clear()
+        self._starts.clear()
+        self._by_start.clear()
 
 
 class HostClientCache(TransportCache):
@@ -286,8 +303,11 @@ class HostShmTransportBuffer(TransportBuffer):
             else:
                 host_pairs.append((tensor, landing))
         _host_move(host_pairs)
-        for dev in devices:
-            _native.stream_sync(dev, None)
+        if devices:
+            from torchstore_b200.transport.hbm import _wait
+
+            for dev in devices:
+                await _wait(dev)  # polled from the loop, like the HBM transport
         self._keep = []
 
     async def handle_put_request(self, ctx: "TransportContext", entries: list[tuple[Request, Any]]) -> list[Any]:
@@ -361,8 +381,11 @@ class HostShmTransportBuffer(TransportBuffer):
                 self._keep = getattr(self, "_keep", []) + [src]
             else:
                 dest.copy_(src)
-        for dev in devices:
-            _native.stream_sync(dev, None)
+        if devices:
+            from torchstore_b200.transport.hbm import _wait
+
+            for dev in devices:
+                await _wait(dev)
         self._keep = []
         return results
 
