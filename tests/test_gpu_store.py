@@ -352,3 +352,39 @@ def test_host_destination_of_other_dtype_is_converted_not_overrun():
             await ts.shutdown()
 
     run(main())
+
+
+def test_host_tier_stages_gpu_tensors_like_the_reference():
+    """TransportType.SharedMemory chosen explicitly on a GPU box: CUDA tensors go D2H into the (pinned)
+    POSIX shm segment and come back H2D, as in the reference (transport/shared_memory.py:374,475); CPU
+    destinations are filled by the native host mover.  Never selected by default when CUDA is present."""
+    from torchstore_b200.transport import TransportType, get_available_transport
+
+    assert get_available_transport(None) == TransportType.NVLink
+
+    async def main():
+        await ts.initialize(num_storage_volumes=1, strategy=ts.LocalRankStrategy(TransportType.SharedMemory))
+        try:
+            t = torch.randn(777, 129, device=DEV)
+            nc = torch.randn(64, 300, device=DEV)[:, 10:200]          # non-contiguous CUDA source
+            await ts.put_batch({"t": t, "nc": nc, "o": {"x": 1}})
+            vol = ts.api.rpc._lookup("torchstore/volume/0")[0]
+            assert not vol.store.kv["t"].is_cuda                        # lives in host shm, not HBM
+            got = await ts.get("t")
+            assert got.device.type == "cpu" and torch.equal(got, t.cpu())
+            dest = torch.zeros(777, 129, device=DEV)
+            out = await ts.get("t", dest)
+            assert out is dest and torch.equal(dest, t)
+            host = torch.zeros(64, 190)
+            await ts.get("nc", host)
+            assert torch.equal(host, nc.cpu())
+            strided = torch.zeros(800, 200, device=DEV)[5:782, 3:132]   # strided CUDA destination
+            await ts.get("t", strided)
+            assert torch.equal(strided, t)
+            t2 = torch.randn(777, 129, device=DEV)
+            await ts.put("t", t2)                                       # in-place overwrite of the segment
+            assert torch.equal(await ts.get("t"), t2.cpu()) and await ts.get("o") == {"x": 1}
+        finally:
+            await ts.shutdown()
+
+    run(main())
