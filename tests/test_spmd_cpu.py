@@ -101,8 +101,8 @@ def _worker(rank, world, port, pg_port, outdir):
     asyncio.run(main())
 
 
-def test_two_rank_spmd_store_on_cpu():
-    world = 2
+@pytest.mark.parametrize("world", [2, 4])
+def test_spmd_store_on_cpu(world):
     port, pg_port = _free_ports(2)
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, port, pg_port, d), nprocs=world, join=True)
@@ -110,7 +110,7 @@ def test_two_rank_spmd_store_on_cpu():
     for r in range(world):
         other = (r + 1) % world
         assert out[r]["peer"] == {"rank": other, "payload": list(range(other + 3))}
-        assert out[r]["keys"][:2] == ["from_0", "from_1"]
+        assert out[r]["keys"][:world] == [f"from_{i}" for i in range(world)]
         assert out[r]["my_volume"] == [str(r)]
         assert out[r]["sd"] == {"step": 11, "cfg": {"a": 1}}
         assert out[r]["exists_missing"] is False
