@@ -84,6 +84,36 @@ def _worker(rank, world, port, pg_port, outdir):
         res["reshard_ok"] = bool(got is dest and torch.equal(dest, full[:, rank * cw:(rank + 1) * cw]))
         res["full_ok"] = bool(torch.equal(await ts.get("w"), full))
         dist.barrier()
+        # real DTensors on a CPU mesh (reference tests/test_tensor_slice.py:150-328, :400-506): put a Shard(0)
+        # DTensor from every rank, read rectangles that span volumes, the whole tensor, and the same key back
+        # under another placement in place; an all-Replicate DTensor is stored as a plain tensor
+        from torch.distributed.device_mesh import init_device_mesh
+        from torch.distributed.tensor import DTensor, Replicate, Shard, distribute_tensor
+
+        from torchstore_b200.controller import ObjectType
+
+        mesh = init_device_mesh("cpu", (world,))
+        cols = 6 if world == 2 else 2 * world  # every rank must own a column under Shard(1) (an empty shard has nothing to fetch)
+        original = torch.arange(4 * world * cols, dtype=torch.float32).reshape(4 * world, cols)
+        await ts.put("dt", distribute_tensor(original, mesh, [Shard(0)]))
+        dist.barrier()
+        cross = TensorSlice((2, 1), (), tuple(original.shape), (4, 4), ())     # spans the volume boundary at row 4
+        single = TensorSlice((1, 0), (), tuple(original.shape), (2, 3), ())    # inside volume 0
+        ok = torch.equal(await ts.get("dt", tensor_slice_spec=cross), original[2:6, 1:5])
+        ok = ok and torch.equal(await ts.get("dt", tensor_slice_spec=single), original[1:3, 0:3])
+        ok = ok and torch.equal(await ts.get("dt"), original)
+        dest_dt = distribute_tensor(torch.zeros_like(original), mesh, [Shard(1)])
+        out = await ts.get("dt", dest_dt)
+        ok = ok and out is dest_dt and torch.equal(dest_dt.to_local(), original.chunk(world, dim=1)[rank])
+        expert = torch.full((16, 8), float(rank))
+        await ts.put(f"expert_{rank}.weight", DTensor.from_local(expert, mesh, [Replicate()], run_check=False))
+        dist.barrier()
+        peer_expert = await ts.get(f"expert_{other}.weight")
+        ok = ok and torch.equal(peer_expert, torch.full((16, 8), float(other)))
+        info = (await c._controller.locate_volumes.call_one([f"expert_{rank}.weight"]))[f"expert_{rank}.weight"]
+        ok = ok and all(v.object_type == ObjectType.TENSOR for v in info.values())
+        res["dtensor_ok"] = bool(ok)
+        dist.barrier()
         await ts.shutdown()
         # the same job can bring the store up again: nothing of the first incarnation leaks in
         await ts.initialize_spmd(ts.LocalRankStrategy())
@@ -114,7 +144,7 @@ def test_spmd_store_on_cpu(world):
         assert out[r]["my_volume"] == [str(r)]
         assert out[r]["sd"] == {"step": 11, "cfg": {"a": 1}}
         assert out[r]["exists_missing"] is False
-        assert out[r]["reshard_ok"] and out[r]["full_ok"]
+        assert out[r]["reshard_ok"] and out[r]["full_ok"] and out[r]["dtensor_ok"]
         assert out[r]["second_keys"] == [] and out[r]["second_peer"] == other
 
 
