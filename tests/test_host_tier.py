@@ -327,3 +327,36 @@ def test_reshard_matrix_matches_the_reference_results_on_the_host_tiers(transpor
 
     run(main())
     assert not _segments()
+
+
+def _leaker(conn):
+    from torchstore_b200 import _native
+
+    name = f"/tsb200_{os.getpid()}_1_leak"
+    _native.shm_create(name, 4096)
+    conn.send(name)  # synchronous: the name is out before we die
+    conn.close()
+    os._exit(0)      # dies without unlinking, like a killed job
+
+
+def test_segments_of_dead_processes_are_reaped():
+    from torchstore_b200.epoch_board import reap_stale_segments
+
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe()
+    p = ctx.Process(target=_leaker, args=(child,))
+    p.start()
+    assert parent.poll(60)
+    name = parent.recv()
+    p.join(30)
+    assert os.path.exists("/dev/shm" + name)
+    mine = f"/tsb200_{os.getpid()}_9_live"
+    from torchstore_b200 import _native
+
+    ptr = _native.shm_create(mine, 4096)
+    try:
+        assert reap_stale_segments() >= 1
+        assert not os.path.exists("/dev/shm" + name) and os.path.exists("/dev/shm" + mine)  # live creators are left alone
+    finally:
+        _native.shm_detach(ptr, 4096)
+        _native.shm_unlink(mine)

@@ -26,6 +26,36 @@ BOARD_BYTES = 4096
 MAX_SLOTS = BOARD_BYTES // 8
 
 
+def reap_stale_segments() -> int:
+    """Unlink /dev/shm segments of this library whose creating process is gone (a killed job cannot
+    unlink its own): names are tsb200_<pid>_... and tsb200_epochs_<pid>_....  Returns how many went."""
+    import re
+
+    gone = 0
+    try:
+        names = os.listdir("/dev/shm")
+    except OSError:
+        return 0
+    for name in names:
+        m = re.match(r"tsb200_(?:epochs_)?(\d+)_", name)
+        if not m:
+            continue
+        pid = int(m.group(1))
+        try:
+            os.kill(pid, 0)
+            continue  # creator alive
+        except ProcessLookupError:
+            pass
+        except PermissionError:
+            continue  # alive, someone else's
+        try:
+            os.unlink(os.path.join("/dev/shm", name))
+            gone += 1
+        except OSError:
+            pass
+    return gone
+
+
 class EpochBoard:
     def __init__(self, name: str, ptr: int, owner: bool):
         self.name, self._ptr, self._owner = name, ptr, owner
@@ -34,6 +64,7 @@ class EpochBoard:
     @classmethod
     def create(cls) -> "EpochBoard | None":
         name = f"/tsb200_epochs_{os.getpid()}_{os.urandom(4).hex()}"
+        reap_stale_segments()
         try:
             ptr = _native.shm_create(name, BOARD_BYTES)
         except Exception as e:  # no /dev/shm, library missing ...: epochs travel by RPC

@@ -114,6 +114,9 @@ class HostVolumeCache(TransportCache):
         self._pending: dict = {}
         self._starts: list[int] = []                     # sorted base addresses of our segments (describe() bisects)
         self._by_start: dict[int, _Segment] = {}
+        from torchstore_b200.epoch_board import reap_stale_segments
+
+        reap_stale_segments()  # segments of killed jobs (their creators could not unlink them)
 
     def allocate(self, shape, dtype: torch.dtype) -> tuple[torch.Tensor, ShmDescriptor]:
         numel = 1
